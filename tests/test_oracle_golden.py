@@ -1,0 +1,137 @@
+"""The oracle against its pins (CPU).  Pins = outputs of the reference's own
+model_definition.py (see tests/golden/make_golden.py); the reference ships none of its own."""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from fun_asr_gguf_b200 import weights as Wm
+from oracle import oracle as O
+from oracle import ref_harness
+from tests import cases
+
+# The oracle uses the same torch ops in the same order as the reference modules, so on the
+# same torch build it reproduces them bit for bit; the tolerance only absorbs a different
+# CPU's kernel selection (oneDNN/MKL code paths differ between ISAs).
+ATOL = 2e-4
+
+
+def _sha(t):
+    return hashlib.sha256(t.contiguous().numpy().tobytes()).hexdigest()[:16]
+
+
+def test_seeded_weights_and_constants_reproduce(golden, weights, consts, planted_weights):
+    meta, _ = golden
+    for k, v in meta["weight_sha"].items():
+        assert _sha(weights[k]) == v, k
+    for k, v in meta["const_sha"].items():
+        assert _sha(consts[k]) == v, k
+    for k, v in meta["planted_sha"].items():
+        got = planted_weights[k]
+        assert got.shape == weights[k].shape
+        if _sha(got) != v:   # planting runs the network; allow last-bit drift on another CPU
+            pytest.skip("planted projection drifted on this CPU; id pins for it are skipped elsewhere")
+
+
+def test_tensor_inventory_matches_reference_count():
+    spec = Wm.tensor_spec()
+    assert len(spec) == 1036
+    assert sum(int(np.prod(s)) for s in spec.values()) == 272807747
+
+
+@pytest.mark.parametrize("name", list(cases.CASES))
+def test_oracle_matches_reference_pins(name, golden, weights, consts, planted_weights):
+    meta, blobs = golden
+    audio, n_valid = cases.build(name)
+    assert _sha(audio) == meta["cases"][name]["audio_sha"]
+    assert np.array_equal(audio.numpy(), blobs[f"{name}.audio"])
+    enc, ad = O.encode_one(audio, n_valid, weights, consts)
+    tl = meta["cases"][name]["target_len"]
+    assert enc.shape[0] == meta["cases"][name]["frames"] == Wm.lfr_frames(audio.shape[0])
+    assert tl == Wm.adaptor_target_len(n_valid) == O.target_len(n_valid)
+    np.testing.assert_allclose(enc.numpy(), blobs[f"{name}.enc"], atol=ATOL, rtol=0)
+    np.testing.assert_allclose(ad[:tl].numpy(), blobs[f"{name}.adaptor"], atol=ATOL, rtol=0)
+    assert float(ad[tl:].abs().sum()) == 0.0
+    t_valid = Wm.lfr_frames(n_valid)
+    assert float(enc[t_valid:].abs().sum()) == 0.0
+    ref_enc = torch.from_numpy(blobs[f"{name}.enc"])
+    ids = O.ctc_ids_one(ref_enc, weights).numpy()
+    margin = blobs[f"{name}.margin"]
+    safe = margin > 1e-3                       # frames whose top-2 gap exceeds re-execution noise
+    assert np.array_equal(ids[safe], blobs[f"{name}.ids"][safe])
+    assert ids.dtype == np.int32
+    ids_p = O.ctc_ids_one(ref_enc, planted_weights).numpy()
+    assert (ids_p != blobs[f"{name}.ids_planted"]).mean() <= 0.02
+
+
+def test_padding_consistency_criterion(weights, consts):
+    """The reference's own stated acceptance bar (experience/01...md:63, 03...md:71-72):
+    padded-vs-native max error at the 1e-5..1e-4 level and cosine > 0.999999."""
+    from tests import signals
+    sig = signals.structured(3 * 16000, 5)
+    e0, a0 = O.encode_one(sig, sig.shape[0], weights, consts)
+    e1, a1 = O.encode_one(signals.padded(sig, 6 * 16000), sig.shape[0], weights, consts)
+    t = e0.shape[0]
+    assert float((e0 - e1[:t]).abs().max()) < 1e-4
+    assert float((a0 - a1[:t]).abs().max()) < 1e-4
+    cos = torch.nn.functional.cosine_similarity(e0.flatten(), e1[:t].flatten(), dim=0)
+    assert float(cos) > 0.999999
+    assert float(e1[t:].abs().sum()) == 0.0
+
+
+def test_ctc_head_is_unmasked(weights, consts):
+    """ids depend on the physical length; an oracle that masked the CTC head
+    would be 'more correct' and wrong."""
+    from tests import signals
+    sig = signals.structured(3 * 16000, 5)
+    e0, _ = O.encode_one(sig, sig.shape[0], weights, consts)
+    e1, _ = O.encode_one(signals.padded(sig, 6 * 16000), sig.shape[0], weights, consts)
+    l0 = O.ctc_logits_one(e0, weights)
+    l1 = O.ctc_logits_one(e1, weights)[: e0.shape[0]]
+    assert float((l0 - l1).abs().max()) > 1e-2
+
+
+def test_batch_is_a_loop_of_rows(weights, consts):
+    from tests import signals
+    a = torch.stack([signals.padded(signals.white(16000, 0), 2 * 16000), signals.white(2 * 16000, 1)])
+    enc, ad = O.encode_batch(a, [16000, 32000], weights, consts)
+    e0, _ = O.encode_one(a[0], 16000, weights, consts)
+    assert torch.equal(enc[0], e0)
+    ids = O.ctc_ids_batch(enc, weights)
+    assert ids.shape == (2, enc.shape[1]) and ids.dtype == torch.int32
+
+
+def test_fp64_arbiter_agrees(weights, consts):
+    audio, n_valid = cases.build("native3")
+    e32, _ = O.encode_one(audio, n_valid, weights, consts)
+    e64, _ = O.encode_one(audio, n_valid, weights, consts, dtype=torch.float64)
+    assert float((e32.double() - e64).abs().max()) < 2e-4
+
+
+def test_greedy_collapse_reference_semantics():
+    blank = 9
+    ids = [9, 9, 3, 3, 9, 3, 4, 4, 4, 9, 9, 5]
+    got = O.greedy_collapse(ids, blank)
+    assert [(t, f) for t, f, _ in got] == [(3, 2), (3, 5), (4, 6), (5, 11)]
+    assert got[0][2] == 0.0 and abs(got[3][2] - (11 * 60 - 240) / 1000) < 1e-12
+    assert O.greedy_collapse([], blank) == []
+
+
+def test_flop_model_matches_survey():
+    assert abs(O.flops(1001) / 1e9 - 705.0) < 0.5
+
+
+@pytest.mark.skipif(not ref_harness.available(), reason="/root/reference not mounted (GPU box)")
+def test_oracle_vs_live_reference(weights, consts):
+    ref = ref_harness.Reference(weights)
+    audio, n_valid = cases.build("ragged")
+    e_r, a_r = ref.encode(audio, n_valid)
+    e_o, a_o = O.encode_one(audio, n_valid, weights, consts)
+    assert float((e_r - e_o).abs().max()) <= 1e-6
+    assert float((a_r - a_o).abs().max()) <= 1e-6
+    assert torch.equal(ref.ctc_ids(e_r), O.ctc_ids_one(e_r, weights))
+    mel_ref = ref.fbank[0]
+    assert torch.equal(mel_ref, consts["const.mel_fbank"])
+    assert torch.equal(ref.stft.cos_kernel[:, 0], consts["const.dft_cos"])
+    assert torch.equal(ref.stft.sin_kernel[:, 0], consts["const.dft_sin"])
