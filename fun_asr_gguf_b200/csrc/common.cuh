@@ -1,0 +1,55 @@
+// Shared host/device helpers for the Fun-ASR-Nano front-half library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+
+namespace fa {
+
+// Geometry of the path. Reference: fun_asr_gguf/model_definition.py:190-200, 223-229 and
+// 01-Export-Encoder-Adaptor-CTC.py:41-45.
+constexpr int kHop = 160, kNfft = 400, kBins = 201, kMels = 80, kLfrM = 7, kLfrN = 6;
+constexpr int kDin = 560, kDenc = 512, kDffn = 2048, kDllm = 1024, kFsmnK = 11;
+constexpr int kEncLayers = 70;
+
+struct Error : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+inline void cuda_check(cudaError_t e, const char* what, const char* file, int line) {
+    if (e != cudaSuccess) {
+        char buf[512];
+        snprintf(buf, sizeof buf, "%s failed: %s (%s:%d)", what, cudaGetErrorString(e), file, line);
+        throw Error(buf);
+    }
+}
+#define FA_CUDA(x) ::fa::cuda_check((x), #x, __FILE__, __LINE__)
+#define FA_REQUIRE(cond, msg)                                                        \
+    do {                                                                             \
+        if (!(cond)) throw ::fa::Error(std::string("requirement failed: ") + (msg)); \
+    } while (0)
+
+inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// Launch accounting: every kernel this library launches goes through FA_LAUNCH so that
+// bench.py can report gpu_launches from a counter instead of an estimate.
+extern thread_local int64_t g_launches;
+#define FA_LAUNCH(kernel, grid, block, smem, stream, ...)            \
+    do {                                                             \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);  \
+        ++::fa::g_launches;                                          \
+        FA_CUDA(cudaGetLastError());                                 \
+    } while (0)
+
+// bf16 "planes": a fp32 value v is carried as hi = bf16(v), lo = bf16(v - hi).  hi+lo keeps
+// 16 mantissa bits, and the three products hi*hi + hi*lo + lo*hi on the tensor cores
+// (fp32 accumulate) reproduce an fp32 GEMM to ~2^-16 relative per product.
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+    hi = __float2bfloat16_rn(v);
+    lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+}  // namespace fa

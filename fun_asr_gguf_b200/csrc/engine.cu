@@ -1,0 +1,639 @@
+// Graph execution: the reference's two exported sessions as sequences of the kernels in this
+// directory.  Layer order and every quirk follow fun_asr_gguf/model_definition.py:
+//   encoder  :205-214 (70 SAN-M layers, after_norm / tp_norm with mask sweeps), layer body :100-116
+//            (layer 0 returns after attention+FSMN: no residual, no FFN — SURVEY F9)
+//   adaptor  :179-185 + :154-163, length control :317-321 (rows >= target_len zeroed — F10)
+//   CTC head :335-337 (5 blocks with mask=None over every physical frame — F7; argmax -> int32)
+// Batches are independent rows (the reference graph is batch-1 only — F8).
+#include "engine.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace fa {
+
+thread_local int64_t g_launches = 0;
+
+namespace {
+constexpr int kLenSlots = 4;
+struct LenRing {
+    cudaEvent_t ev[kLenSlots];
+    int next = 0;
+};
+std::map<const Context*, LenRing> g_rings;
+
+int lfr_frames_of(int64_t samples) { return (int)((samples / kHop + 1 + kLfrN - 1) / kLfrN); }
+int target_len_of(int64_t n_valid) {
+    const int t = lfr_frames_of(n_valid);
+    const int o1 = 1 + (t - 3 + 2) / 2;                  // floor division on non-negative operands only when t >= 1
+    return (1 + (o1 - 3 + 2) / 2 - 1) / 2 + 1;
+}
+}  // namespace
+
+// ------------------------------------------------------------------------------------ construction
+
+Context::Context(int device, int max_batch, int64_t max_samples, int precision)
+    : device_(device), max_batch_(max_batch), prec_(precision), max_samples_(max_samples) {
+    FA_REQUIRE(max_batch >= 1 && max_samples >= 1, "max_batch and max_samples must be positive");
+    FA_REQUIRE(precision >= kFp32 && precision <= kBf16, "unknown precision mode");
+    int count = 0;
+    FA_CUDA(cudaGetDeviceCount(&count));
+    FA_REQUIRE(device >= 0 && device < count, "no such CUDA device");
+    set_device();
+    cudaDeviceProp prop;
+    FA_CUDA(cudaGetDeviceProperties(&prop, device));
+    FA_REQUIRE(prop.major == 10, "this library is built for sm_100a (B200) only; found compute capability " +
+                                     std::to_string(prop.major) + "." + std::to_string(prop.minor));
+    FA_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    frontend_init_device();
+    attention_init_device();
+    tc_init_device();
+    t_mel_max_ = (int)(max_samples / kHop + 1);
+    t_max_ = lfr_frames_of(max_samples);
+    m_max_ = (int64_t)max_batch * t_max_;
+    LenRing& r = g_rings[this];
+    for (auto& e : r.ev) FA_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+}
+
+Context::~Context() {
+    cudaSetDevice(device_);
+    cudaDeviceSynchronize();
+    auto it = g_rings.find(this);
+    if (it != g_rings.end()) {
+        for (auto& e : it->second.ev) cudaEventDestroy(e);
+        g_rings.erase(it);
+    }
+    if (h_lens_) cudaFreeHost(h_lens_);
+    if (own_stream_ && stream_) cudaStreamDestroy(stream_);
+}
+
+void Context::set_stream(cudaStream_t s) {
+    set_device();
+    FA_CUDA(cudaStreamSynchronize(stream_));
+    if (own_stream_ && stream_) cudaStreamDestroy(stream_);
+    stream_ = s;
+    own_stream_ = false;
+}
+
+void Context::load_tensor(const std::string& name, const float* host, const std::vector<int64_t>& shape) {
+    FA_REQUIRE(!finalized_, "context already finalized");
+    set_device();
+    size_t n = 1;
+    for (auto d : shape) { FA_REQUIRE(d > 0, "tensor dims must be positive"); n *= (size_t)d; }
+    HostTensor t;
+    t.shape = shape;
+    t.buf.reset(new DevBuf);
+    t.buf->alloc(n * sizeof(float));
+    FA_CUDA(cudaMemcpy(t.buf->p, host, n * sizeof(float), cudaMemcpyHostToDevice));
+    tensors_[name] = std::move(t);
+}
+
+const float* Context::T(const std::string& name, std::vector<int64_t> shape) const {
+    auto it = tensors_.find(name);
+    if (it == tensors_.end()) throw Error("missing tensor: " + name);
+    if (it->second.shape != shape) {
+        std::string got, want;
+        for (auto d : it->second.shape) got += std::to_string(d) + ",";
+        for (auto d : shape) want += std::to_string(d) + ",";
+        throw Error("tensor " + name + " has shape (" + got + ") but the path needs (" + want + ")");
+    }
+    return it->second.buf->as<float>();
+}
+
+void Context::build_planes(Linear& l) {
+    if (prec_ == kFp32) return;
+    derived_.emplace_back(new DevBuf);
+    DevBuf& b = *derived_.back();
+    const int64_t n = (int64_t)l.n * l.k;
+    b.alloc(2 * n * sizeof(__nv_bfloat16));
+    l.planes = b.as<__nv_bfloat16>();
+    launch_split_planes(l.w, n, Planes{l.planes, l.planes + n}, stream_);
+    l.op = tc_make_operand(l.planes, l.n, l.k, l.k, n, 2, kTcBlockN);
+}
+
+Linear Context::make_linear_from(const float* w, const float* b, int n, int k) {
+    Linear l;
+    l.w = w; l.b = b; l.n = n; l.k = k;
+    build_planes(l);
+    return l;
+}
+
+Linear Context::make_linear(const std::string& prefix, int n, int k) {
+    return make_linear_from(T(prefix + ".weight", {n, k}), T(prefix + ".bias", {n}), n, k);
+}
+
+void Context::finalize() {
+    FA_REQUIRE(!finalized_, "context already finalized");
+    set_device();
+    // ---- encoder
+    auto sanm = [&](const std::string& p, int d_in) {
+        SanmLayer L;
+        L.d_in = d_in;
+        L.ln1_g = T(p + ".norm1.weight", {d_in});
+        L.ln1_b = T(p + ".norm1.bias", {d_in});
+        L.ln2_g = T(p + ".norm2.weight", {kDenc});
+        L.ln2_b = T(p + ".norm2.bias", {kDenc});
+        L.fsmn_w = T(p + ".self_attn.fsmn_block.weight", {kDenc, 1, kFsmnK});
+        L.qkv = make_linear(p + ".self_attn.linear_q_k_v", 3 * kDenc, d_in);
+        L.out = make_linear(p + ".self_attn.linear_out", kDenc, kDenc);
+        if (d_in == kDenc) {      // layer 0's FFN / norm2 exist in the checkpoint but are never executed (F9)
+            L.w1 = make_linear(p + ".feed_forward.w_1", kDffn, kDenc);
+            L.w2 = make_linear(p + ".feed_forward.w_2", kDenc, kDffn);
+        }
+        return L;
+    };
+    enc_layers_.clear();
+    enc_layers_.push_back(sanm("audio_encoder.encoders0.0", kDin));
+    for (int i = 0; i < 49; ++i) enc_layers_.push_back(sanm("audio_encoder.encoders." + std::to_string(i), kDenc));
+    for (int i = 0; i < 20; ++i) enc_layers_.push_back(sanm("audio_encoder.tp_encoders." + std::to_string(i), kDenc));
+    after_g_ = T("audio_encoder.after_norm.weight", {kDenc});
+    after_b_ = T("audio_encoder.after_norm.bias", {kDenc});
+    tp_g_ = T("audio_encoder.tp_norm.weight", {kDenc});
+    tp_b_ = T("audio_encoder.tp_norm.bias", {kDenc});
+
+    // ---- adaptor / CTC decoder (CorrectTransformerAdaptor): q|k|v stacked into one [3d][d] projection
+    auto proj = [&](const std::string& p, int d, int n_blocks, int heads) {
+        Projector P;
+        P.d = d; P.heads = heads;
+        P.lin1 = make_linear(p + ".linear1", kDffn, kDenc);
+        P.lin2 = make_linear(p + ".linear2", d, kDffn);
+        for (int i = 0; i < n_blocks; ++i) {
+            const std::string b = p + ".blocks." + std::to_string(i);
+            MhaBlock B;
+            B.ln1_g = T(b + ".norm1.weight", {d}); B.ln1_b = T(b + ".norm1.bias", {d});
+            B.ln2_g = T(b + ".norm2.weight", {d}); B.ln2_b = T(b + ".norm2.bias", {d});
+            derived_.emplace_back(new DevBuf);
+            DevBuf& wq = *derived_.back();
+            wq.alloc(((size_t)3 * d * d + 3 * d) * sizeof(float));
+            float* w = wq.as<float>();
+            float* bias = w + (size_t)3 * d * d;
+            const char* names[3] = {"linear_q", "linear_k", "linear_v"};
+            for (int j = 0; j < 3; ++j) {
+                const std::string n = b + ".self_attn." + names[j];
+                FA_CUDA(cudaMemcpyAsync(w + (size_t)j * d * d, T(n + ".weight", {d, d}), (size_t)d * d * sizeof(float),
+                                        cudaMemcpyDeviceToDevice, stream_));
+                FA_CUDA(cudaMemcpyAsync(bias + j * d, T(n + ".bias", {d}), d * sizeof(float), cudaMemcpyDeviceToDevice,
+                                        stream_));
+            }
+            B.qkv = make_linear_from(w, bias, 3 * d, d);
+            B.out = make_linear(b + ".self_attn.linear_out", d, d);
+            B.w1 = make_linear(b + ".feed_forward.w_1", d / 4, d);
+            B.w2 = make_linear(b + ".feed_forward.w_2", d, d / 4);
+            P.blocks.push_back(B);
+        }
+        return P;
+    };
+    adaptor_ = proj("audio_adaptor", kDllm, 2, 8);
+    ctc_ = proj("ctc_decoder", kDenc, 5, 8);
+    {
+        auto it = tensors_.find("ctc_proj.ctc_lo.weight");
+        if (it == tensors_.end() || it->second.shape.size() != 2 || it->second.shape[1] != kDenc)
+            throw Error("missing or malformed tensor: ctc_proj.ctc_lo.weight");
+        vocab_ = (int)it->second.shape[0];
+        ctc_lo_ = make_linear("ctc_proj.ctc_lo", vocab_, kDenc);
+    }
+
+    // ---- front-end constants: DFT kernels transposed to [n][cos|sin] and the mel matrix to [bin][mel]
+    {
+        const float* c = T("const.dft_cos", {kBins, kNfft});
+        const float* s = T("const.dft_sin", {kBins, kNfft});
+        const float* mf = T("const.mel_fbank", {kMels, kBins});
+        std::vector<float> hc((size_t)kBins * kNfft), hs(hc.size()), hm((size_t)kMels * kBins);
+        FA_CUDA(cudaMemcpy(hc.data(), c, hc.size() * 4, cudaMemcpyDeviceToHost));
+        FA_CUDA(cudaMemcpy(hs.data(), s, hs.size() * 4, cudaMemcpyDeviceToHost));
+        FA_CUDA(cudaMemcpy(hm.data(), mf, hm.size() * 4, cudaMemcpyDeviceToHost));
+        std::vector<float> dt((size_t)kNfft * kDftLd, 0.f), mt((size_t)kBins * kMels);
+        for (int k = 0; k < kBins; ++k)
+            for (int n = 0; n < kNfft; ++n) {
+                dt[(size_t)n * kDftLd + k] = hc[(size_t)k * kNfft + n];
+                dt[(size_t)n * kDftLd + kBins + k] = hs[(size_t)k * kNfft + n];
+            }
+        for (int j = 0; j < kMels; ++j)
+            for (int k = 0; k < kBins; ++k) mt[(size_t)k * kMels + j] = hm[(size_t)j * kBins + k];
+        derived_.emplace_back(new DevBuf);
+        derived_.back()->alloc(dt.size() * 4);
+        FA_CUDA(cudaMemcpy(derived_.back()->p, dt.data(), dt.size() * 4, cudaMemcpyHostToDevice));
+        dft_t_ = derived_.back()->as<float>();
+        derived_.emplace_back(new DevBuf);
+        derived_.back()->alloc(mt.size() * 4);
+        FA_CUDA(cudaMemcpy(derived_.back()->p, mt.data(), mt.size() * 4, cudaMemcpyHostToDevice));
+        melfb_t_ = derived_.back()->as<float>();
+        auto it = tensors_.find("const.pos_enc");
+        if (it == tensors_.end() || it->second.shape.size() != 2 || it->second.shape[1] != kDin)
+            throw Error("missing or malformed tensor: const.pos_enc");
+        pos_rows_ = (int)it->second.shape[0];
+        FA_REQUIRE(pos_rows_ >= t_max_, "const.pos_enc has fewer rows than the longest segment needs");
+        pos_enc_ = it->second.buf->as<float>();
+    }
+
+    // ---- workspace, sized for max_batch segments of max_samples
+    const size_t M = (size_t)m_max_;
+    const bool tc = prec_ != kFp32;
+    audio_.alloc((size_t)max_batch_ * max_samples_ * 4);
+    partials_.alloc((size_t)max_batch_ * kMeanParts * 8);
+    logmel_.alloc((size_t)max_batch_ * t_mel_max_ * kMels * 4);
+    x0_.alloc(M * kDin * 4);
+    x_.alloc(M * kDllm * 4);
+    qkv_.alloc(M * 3 * kDllm * 4);
+    enc_.alloc(M * kDenc * 4);
+    adaptor_out_.alloc(M * kDllm * 4);
+    ids_.alloc(M * 4);
+    tokens_.alloc(M * 4 * 2 + (size_t)max_batch_ * 4);
+    if (tc) {
+        hpl_.alloc(2 * M * kDllm * 2);
+        ctxpl_.alloc(2 * M * kDllm * 2);
+        ffnpl_.alloc(2 * M * kDffn * 2);
+        encpl_.alloc(2 * M * kDenc * 2);
+        const size_t tiles = (size_t)tc_argmax_tiles(vocab_);
+        amax_val_.alloc(M * tiles * 4);
+        amax_idx_.alloc(M * tiles * 4);
+    } else {
+        h32_.alloc(M * kDllm * 4);
+        ctx32_.alloc(M * kDllm * 4);
+        ffn32_.alloc(M * kDffn * 4);
+        logits_rows_ = (int)std::min<size_t>(M, 2048);
+        logits_.alloc((size_t)logits_rows_ * vocab_ * 4);
+    }
+    lens_.alloc((size_t)3 * max_batch_ * sizeof(int));
+    d_nvalid_ = lens_.as<int>();
+    d_tvalid_ = d_nvalid_ + max_batch_;
+    d_tlen_ = d_tvalid_ + max_batch_;
+    FA_CUDA(cudaMallocHost(&h_lens_, (size_t)kLenSlots * 3 * max_batch_ * sizeof(int)));
+    FA_CUDA(cudaStreamSynchronize(stream_));
+    finalized_ = true;
+}
+
+// ------------------------------------------------------------------------------------ helpers
+
+Act Context::h_act(int ld) const {
+    Act a; a.ld = ld; a.f32 = h32_.as<float>();
+    if (hpl_.p) a.pl = Planes{hpl_.as<__nv_bfloat16>(), hpl_.as<__nv_bfloat16>() + m_max_ * kDllm};
+    return a;
+}
+Act Context::ctx_act(int ld) const {
+    Act a; a.ld = ld; a.f32 = ctx32_.as<float>();
+    if (ctxpl_.p) a.pl = Planes{ctxpl_.as<__nv_bfloat16>(), ctxpl_.as<__nv_bfloat16>() + m_max_ * kDllm};
+    return a;
+}
+Act Context::ffn_act(int ld) const {
+    Act a; a.ld = ld; a.f32 = ffn32_.as<float>();
+    if (ffnpl_.p) a.pl = Planes{ffnpl_.as<__nv_bfloat16>(), ffnpl_.as<__nv_bfloat16>() + m_max_ * kDffn};
+    return a;
+}
+
+static Epilogue into(const Act& dst, bool fp32_mode) {
+    Epilogue e;
+    if (fp32_mode) { e.out_f32 = const_cast<float*>(dst.f32); e.ldc = dst.ld; }
+    else { e.out_pl = dst.pl; e.ldp = dst.ld; }
+    return e;
+}
+
+void Context::linear(const Act& a, const Linear& w, int m, const Epilogue& ep_in) {
+    Epilogue ep = ep_in;
+    ep.bias = w.b;
+    if (prec_ == kFp32) {
+        launch_gemm_simt(a.f32, a.ld, w.w, m, w.n, w.k, ep, stream_);
+    } else {
+        const int64_t plane_stride = a.pl.lo - a.pl.hi;
+        const TcOperand opa = tc_make_operand(a.pl.hi, m, w.k, a.ld, plane_stride, 2, kTcBlockM);
+        launch_gemm_tc(opa, w.op, m, w.n, w.k, prec_ == kBf16x3 ? 2 : 1, ep, stream_);
+    }
+}
+
+void Context::attention(const float* qkv, int ld, int d_model, int batch, int frames, int heads, const int* kv_len,
+                        float* ctx_f32, Planes ctx_pl, int ldo) {
+    launch_attention_simt(qkv, qkv + d_model, qkv + 2 * d_model, ld, batch, frames, heads, d_model / heads, kv_len,
+                          ctx_f32, ctx_pl, ldo, stream_);
+}
+
+void Context::tap(const char* name, const float* d, int64_t rows, int64_t cols) {
+    if (!taps_on_) return;
+    auto& slot = taps_[name];
+    slot.first = {rows, cols};
+    slot.second.reset(new DevBuf);
+    slot.second->alloc((size_t)rows * cols * 4);
+    FA_CUDA(cudaMemcpyAsync(slot.second->p, d, (size_t)rows * cols * 4, cudaMemcpyDeviceToDevice, stream_));
+}
+
+bool Context::read_tap(const std::string& name, std::vector<float>& out, std::vector<int64_t>& shape) {
+    auto it = taps_.find(name);
+    if (it == taps_.end()) return false;
+    sync();
+    shape = it->second.first;
+    out.resize((size_t)shape[0] * shape[1]);
+    FA_CUDA(cudaMemcpy(out.data(), it->second.second->p, out.size() * 4, cudaMemcpyDeviceToHost));
+    return true;
+}
+
+std::vector<std::string> Context::tap_names() const {
+    std::vector<std::string> v;
+    for (auto& kv : taps_) v.push_back(kv.first);
+    return v;
+}
+
+void Context::ensure_room(int batch, int64_t s_phys) const {
+    FA_REQUIRE(finalized_, "context not finalized (load every tensor, then fa_ctx_finalize)");
+    FA_REQUIRE(batch >= 1 && batch <= max_batch_, "batch exceeds the context's max_batch");
+    FA_REQUIRE(s_phys >= 1 && s_phys <= max_samples_, "segment longer than the context's max_samples");
+}
+
+// ------------------------------------------------------------------------------------ layers
+
+void Context::sanm_layer(const SanmLayer& L, bool first, int batch, int frames) {
+    const int M = batch * frames;
+    const bool f32 = prec_ == kFp32;
+    float* x = x_.as<float>();
+    const float* xin = first ? x0_.as<float>() : x;
+    const Act h = h_act(L.d_in);
+    launch_layernorm(xin, M, L.d_in, L.ln1_g, L.ln1_b, 1e-5f, nullptr, frames, f32 ? const_cast<float*>(h.f32) : nullptr,
+                     f32 ? Planes{} : h.pl, stream_);
+    Epilogue e;
+    e.out_f32 = qkv_.as<float>(); e.ldc = 3 * kDenc;
+    linear(h, L.qkv, M, e);
+    const float* qkv = qkv_.as<float>();
+    // x <- (x) + fsmn(v*m): the memory branch plus, except in layer 0, the block's residual
+    launch_fsmn(qkv + 2 * kDenc, 3 * kDenc, L.fsmn_w, d_tvalid_, batch, frames, first ? nullptr : x, x, stream_);
+    const Act c = ctx_act(kDenc);
+    attention(qkv, 3 * kDenc, kDenc, batch, frames, 4, d_tvalid_, f32 ? const_cast<float*>(c.f32) : nullptr,
+              f32 ? Planes{} : c.pl, kDenc);
+    Epilogue eo;
+    eo.resid = x; eo.ldr = kDenc; eo.out_f32 = x; eo.ldc = kDenc;
+    linear(c, L.out, M, eo);
+    if (first) return;
+    const Act h2 = h_act(kDenc);
+    launch_layernorm(x, M, kDenc, L.ln2_g, L.ln2_b, 1e-5f, nullptr, frames, f32 ? const_cast<float*>(h2.f32) : nullptr,
+                     f32 ? Planes{} : h2.pl, stream_);
+    const Act f = ffn_act(kDffn);
+    Epilogue e1 = into(f, f32);
+    e1.relu = true;
+    linear(h2, L.w1, M, e1);
+    Epilogue e2;
+    e2.resid = x; e2.ldr = kDenc; e2.out_f32 = x; e2.ldc = kDenc;
+    linear(f, L.w2, M, e2);
+}
+
+void Context::projector(const Projector& P, const Act& in, int batch, int frames, const int* kv_len) {
+    const int M = batch * frames, d = P.d;
+    const bool f32 = prec_ == kFp32;
+    float* x = x_.as<float>();
+    const Act f = ffn_act(kDffn);
+    Epilogue e1 = into(f, f32);
+    e1.relu = true;
+    linear(in, P.lin1, M, e1);
+    Epilogue e2;
+    e2.out_f32 = x; e2.ldc = d;
+    linear(f, P.lin2, M, e2);
+    for (const MhaBlock& B : P.blocks) {
+        const Act h = h_act(d);
+        launch_layernorm(x, M, d, B.ln1_g, B.ln1_b, 1e-12f, nullptr, frames, f32 ? const_cast<float*>(h.f32) : nullptr,
+                         f32 ? Planes{} : h.pl, stream_);
+        Epilogue eq;
+        eq.out_f32 = qkv_.as<float>(); eq.ldc = 3 * d;
+        linear(h, B.qkv, M, eq);
+        const Act c = ctx_act(d);
+        attention(qkv_.as<float>(), 3 * d, d, batch, frames, P.heads, kv_len, f32 ? const_cast<float*>(c.f32) : nullptr,
+                  f32 ? Planes{} : c.pl, d);
+        Epilogue eo;
+        eo.resid = x; eo.ldr = d; eo.out_f32 = x; eo.ldc = d;
+        linear(c, B.out, M, eo);
+        launch_layernorm(x, M, d, B.ln2_g, B.ln2_b, 1e-12f, nullptr, frames, f32 ? const_cast<float*>(h.f32) : nullptr,
+                         f32 ? Planes{} : h.pl, stream_);
+        const Act ff = ffn_act(d / 4);
+        Epilogue ea = into(ff, f32);
+        ea.relu = true;
+        linear(h, B.w1, M, ea);
+        Epilogue eb;
+        eb.resid = x; eb.ldr = d; eb.out_f32 = x; eb.ldc = d;
+        linear(ff, B.w2, M, eb);
+    }
+}
+
+// ------------------------------------------------------------------------------------ graphs
+
+void Context::encode_dev(const float* d_audio, int batch, int64_t s_phys, const int64_t* h_ilens, float* d_enc,
+                         float* d_adaptor) {
+    ensure_room(batch, s_phys);
+    set_device();
+    const int t_mel = (int)(s_phys / kHop + 1), frames = lfr_frames_of(s_phys), M = batch * frames;
+    LenRing& ring = g_rings[this];
+    const int slot = ring.next;
+    ring.next = (ring.next + 1) % kLenSlots;
+    FA_CUDA(cudaEventSynchronize(ring.ev[slot]));
+    int* hl = h_lens_ + (size_t)slot * 3 * max_batch_;
+    for (int b = 0; b < batch; ++b) {
+        const int64_t nv = h_ilens[b];
+        FA_REQUIRE(nv >= 1 && nv <= s_phys, "ilens must satisfy 1 <= ilens[b] <= samples");
+        hl[b] = (int)nv;
+        hl[max_batch_ + b] = lfr_frames_of(nv);
+        hl[2 * max_batch_ + b] = target_len_of(nv);
+    }
+    FA_CUDA(cudaMemcpyAsync(lens_.p, hl, (size_t)3 * max_batch_ * sizeof(int), cudaMemcpyHostToDevice, stream_));
+    FA_CUDA(cudaEventRecord(ring.ev[slot], stream_));
+
+    launch_segment_sums(d_audio, batch, s_phys, d_nvalid_, partials_.as<double>(), stream_);
+    launch_fbank(d_audio, batch, s_phys, d_nvalid_, partials_.as<double>(), dft_t_, melfb_t_, logmel_.as<float>(), t_mel,
+                 stream_);
+    tap("logmel", logmel_.as<float>(), (int64_t)batch * t_mel, kMels);
+    float* lfr_raw = taps_on_ ? adaptor_out_.as<float>() : nullptr;     // borrowed scratch for the tap
+    launch_lfr_embed(logmel_.as<float>(), batch, t_mel, frames, d_nvalid_, pos_enc_, x0_.as<float>(), lfr_raw, stream_);
+    if (lfr_raw) tap("lfr", lfr_raw, M, kDin);
+
+    float* x = x_.as<float>();
+    for (int i = 0; i < kEncLayers; ++i) {
+        sanm_layer(enc_layers_[i], i == 0, batch, frames);
+        if (i == 0) tap("layer0", x, M, kDenc);
+        if (i == 1) tap("layer1", x, M, kDenc);
+        if (i == 49) {
+            launch_layernorm(x, M, kDenc, after_g_, after_b_, 1e-5f, d_tvalid_, frames, x, Planes{}, stream_);
+            tap("layer49", x, M, kDenc);
+        }
+    }
+    const bool f32 = prec_ == kFp32;
+    Planes encpl;
+    if (!f32) encpl = Planes{encpl_.as<__nv_bfloat16>(), encpl_.as<__nv_bfloat16>() + m_max_ * kDenc};
+    launch_layernorm(x, M, kDenc, tp_g_, tp_b_, 1e-5f, d_tvalid_, frames, d_enc, encpl, stream_);
+
+    Act in; in.f32 = d_enc; in.pl = encpl; in.ld = kDenc;
+    projector(adaptor_, in, batch, frames, d_tvalid_);
+    launch_row_keep(x, d_adaptor, batch, frames, kDllm, d_tlen_, stream_);
+}
+
+void Context::ctc_dev(const float* d_enc, int batch, int frames, int32_t* d_ids) {
+    FA_REQUIRE(finalized_, "context not finalized");
+    FA_REQUIRE(batch >= 1 && batch <= max_batch_ && frames >= 1 && frames <= t_max_, "CTC input exceeds the context's capacity");
+    set_device();
+    const int M = batch * frames;
+    const bool f32 = prec_ == kFp32;
+    Act in; in.f32 = d_enc; in.ld = kDenc;
+    if (!f32) {
+        in.pl = Planes{encpl_.as<__nv_bfloat16>(), encpl_.as<__nv_bfloat16>() + m_max_ * kDenc};
+        launch_split_planes(d_enc, (int64_t)M * kDenc, in.pl, stream_);
+    }
+    projector(ctc_, in, batch, frames, nullptr);
+    float* x = x_.as<float>();
+    tap("ctc_h", x, M, kDenc);
+    if (f32) {
+        for (int r0 = 0; r0 < M; r0 += logits_rows_) {
+            const int rows = std::min(logits_rows_, M - r0);
+            Epilogue e;
+            e.bias = ctc_lo_.b; e.out_f32 = logits_.as<float>(); e.ldc = vocab_;
+            launch_gemm_simt(x + (size_t)r0 * kDenc, kDenc, ctc_lo_.w, rows, vocab_, kDenc, e, stream_);
+            launch_argmax_rows(logits_.as<float>(), rows, vocab_, vocab_, d_ids + r0, stream_);
+        }
+    } else {
+        // the logits never reach HBM: the GEMM epilogue keeps a running (max, argmax) per 256-column tile
+        const Act h = h_act(kDenc);
+        launch_split_planes(x, (int64_t)M * kDenc, h.pl, stream_);
+        Epilogue e;
+        e.amax_val = amax_val_.as<float>(); e.amax_idx = amax_idx_.as<int32_t>();
+        linear(h, ctc_lo_, M, e);
+        launch_argmax_combine(amax_val_.as<float>(), amax_idx_.as<int32_t>(), M, tc_argmax_tiles(vocab_), d_ids, stream_);
+    }
+}
+
+void Context::collapse_dev(const int32_t* d_ids, int batch, int frames, int32_t* d_tokens, int32_t* d_starts,
+                           int32_t* d_counts) {
+    set_device();
+    launch_ctc_collapse(d_ids, batch, frames, vocab_ - 1, d_tokens, d_starts, d_counts, stream_);
+}
+
+void Context::encode_host(const float* audio, int batch, int64_t s_phys, const int64_t* ilens, float* enc,
+                          float* adaptor) {
+    ensure_room(1, s_phys);
+    set_device();
+    const int frames = lfr_frames_of(s_phys);
+    for (int b0 = 0; b0 < batch; b0 += max_batch_) {
+        const int nb = std::min(max_batch_, batch - b0);
+        FA_CUDA(cudaMemcpyAsync(audio_.p, audio + (size_t)b0 * s_phys, (size_t)nb * s_phys * 4, cudaMemcpyHostToDevice, stream_));
+        encode_dev(audio_.as<float>(), nb, s_phys, ilens + b0, enc_.as<float>(), adaptor_out_.as<float>());
+        FA_CUDA(cudaMemcpyAsync(enc + (size_t)b0 * frames * kDenc, enc_.p, (size_t)nb * frames * kDenc * 4, cudaMemcpyDeviceToHost, stream_));
+        FA_CUDA(cudaMemcpyAsync(adaptor + (size_t)b0 * frames * kDllm, adaptor_out_.p, (size_t)nb * frames * kDllm * 4, cudaMemcpyDeviceToHost, stream_));
+        FA_CUDA(cudaStreamSynchronize(stream_));
+    }
+}
+
+void Context::ctc_host(const float* enc, int batch, int frames, int32_t* ids) {
+    set_device();
+    for (int b0 = 0; b0 < batch; b0 += max_batch_) {
+        const int nb = std::min(max_batch_, batch - b0);
+        FA_CUDA(cudaMemcpyAsync(enc_.p, enc + (size_t)b0 * frames * kDenc, (size_t)nb * frames * kDenc * 4, cudaMemcpyHostToDevice, stream_));
+        ctc_dev(enc_.as<float>(), nb, frames, ids_.as<int32_t>());
+        FA_CUDA(cudaMemcpyAsync(ids + (size_t)b0 * frames, ids_.p, (size_t)nb * frames * 4, cudaMemcpyDeviceToHost, stream_));
+        FA_CUDA(cudaStreamSynchronize(stream_));
+    }
+}
+
+void Context::front_half_host(const float* audio, int batch, int64_t s_phys, const int64_t* ilens, float* enc,
+                              float* adaptor, int32_t* ids) {
+    ensure_room(1, s_phys);
+    set_device();
+    const int frames = lfr_frames_of(s_phys);
+    for (int b0 = 0; b0 < batch; b0 += max_batch_) {
+        const int nb = std::min(max_batch_, batch - b0);
+        FA_CUDA(cudaMemcpyAsync(audio_.p, audio + (size_t)b0 * s_phys, (size_t)nb * s_phys * 4, cudaMemcpyHostToDevice, stream_));
+        encode_dev(audio_.as<float>(), nb, s_phys, ilens + b0, enc_.as<float>(), adaptor_out_.as<float>());
+        if (enc) FA_CUDA(cudaMemcpyAsync(enc + (size_t)b0 * frames * kDenc, enc_.p, (size_t)nb * frames * kDenc * 4, cudaMemcpyDeviceToHost, stream_));
+        if (adaptor) FA_CUDA(cudaMemcpyAsync(adaptor + (size_t)b0 * frames * kDllm, adaptor_out_.p, (size_t)nb * frames * kDllm * 4, cudaMemcpyDeviceToHost, stream_));
+        ctc_dev(enc_.as<float>(), nb, frames, ids_.as<int32_t>());
+        FA_CUDA(cudaMemcpyAsync(ids + (size_t)b0 * frames, ids_.p, (size_t)nb * frames * 4, cudaMemcpyDeviceToHost, stream_));
+        FA_CUDA(cudaStreamSynchronize(stream_));
+    }
+}
+
+// ------------------------------------------------------------------------------------ kernel-level test hooks
+
+void Context::test_linear(const float* a, const float* w, const float* bias, const float* resid, int m, int n, int k,
+                          int relu, int precision, float* out, float* out_planes_sum) {
+    set_device();
+    DevBuf da, dw, db, dr, dout, dpl_a, dpl_w, dpl_o;
+    da.alloc((size_t)m * k * 4); dw.alloc((size_t)n * k * 4); db.alloc((size_t)n * 4); dout.alloc((size_t)m * n * 4);
+    FA_CUDA(cudaMemcpy(da.p, a, da.bytes, cudaMemcpyHostToDevice));
+    FA_CUDA(cudaMemcpy(dw.p, w, dw.bytes, cudaMemcpyHostToDevice));
+    FA_CUDA(cudaMemcpy(db.p, bias, db.bytes, cudaMemcpyHostToDevice));
+    if (resid) { dr.alloc((size_t)m * n * 4); FA_CUDA(cudaMemcpy(dr.p, resid, dr.bytes, cudaMemcpyHostToDevice)); }
+    Epilogue e;
+    e.bias = db.as<float>(); e.resid = dr.as<float>(); e.ldr = n; e.relu = relu != 0; e.out_f32 = dout.as<float>(); e.ldc = n;
+    const int ldp = (n + 7) / 8 * 8;
+    if (out_planes_sum) {
+        dpl_o.alloc((size_t)2 * m * ldp * 2);
+        FA_CUDA(cudaMemsetAsync(dpl_o.p, 0, dpl_o.bytes, stream_));
+        e.out_pl = Planes{dpl_o.as<__nv_bfloat16>(), dpl_o.as<__nv_bfloat16>() + (size_t)m * ldp};
+        e.ldp = ldp;
+    }
+    if (precision == kFp32) {
+        launch_gemm_simt(da.as<float>(), k, dw.as<float>(), m, n, k, e, stream_);
+    } else {
+        dpl_a.alloc((size_t)2 * m * k * 2); dpl_w.alloc((size_t)2 * n * k * 2);
+        Planes pa{dpl_a.as<__nv_bfloat16>(), dpl_a.as<__nv_bfloat16>() + (size_t)m * k};
+        Planes pw{dpl_w.as<__nv_bfloat16>(), dpl_w.as<__nv_bfloat16>() + (size_t)n * k};
+        launch_split_planes(da.as<float>(), (int64_t)m * k, pa, stream_);
+        launch_split_planes(dw.as<float>(), (int64_t)n * k, pw, stream_);
+        const TcOperand oa = tc_make_operand(pa.hi, m, k, k, (int64_t)m * k, 2, kTcBlockM);
+        const TcOperand ow = tc_make_operand(pw.hi, n, k, k, (int64_t)n * k, 2, kTcBlockN);
+        launch_gemm_tc(oa, ow, m, n, k, precision == kBf16x3 ? 2 : 1, e, stream_);
+    }
+    FA_CUDA(cudaStreamSynchronize(stream_));
+    FA_CUDA(cudaMemcpy(out, dout.p, dout.bytes, cudaMemcpyDeviceToHost));
+    if (out_planes_sum) {
+        std::vector<__nv_bfloat16> hp((size_t)2 * m * ldp);
+        FA_CUDA(cudaMemcpy(hp.data(), dpl_o.p, dpl_o.bytes, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < m; ++i)
+            for (int j = 0; j < n; ++j)
+                out_planes_sum[(size_t)i * n + j] = __bfloat162float(hp[(size_t)i * ldp + j]) +
+                                                    __bfloat162float(hp[(size_t)m * ldp + (size_t)i * ldp + j]);
+    }
+}
+
+void Context::test_vocab_argmax(const float* a, const float* w, const float* bias, int m, int n, int k, int precision,
+                                int32_t* ids) {
+    set_device();
+    DevBuf da, dw, db, dids;
+    da.alloc((size_t)m * k * 4); dw.alloc((size_t)n * k * 4); db.alloc((size_t)n * 4); dids.alloc((size_t)m * 4);
+    FA_CUDA(cudaMemcpy(da.p, a, da.bytes, cudaMemcpyHostToDevice));
+    FA_CUDA(cudaMemcpy(dw.p, w, dw.bytes, cudaMemcpyHostToDevice));
+    FA_CUDA(cudaMemcpy(db.p, bias, db.bytes, cudaMemcpyHostToDevice));
+    if (precision == kFp32) {
+        DevBuf dl;
+        dl.alloc((size_t)m * n * 4);
+        Epilogue e;
+        e.bias = db.as<float>(); e.out_f32 = dl.as<float>(); e.ldc = n;
+        launch_gemm_simt(da.as<float>(), k, dw.as<float>(), m, n, k, e, stream_);
+        launch_argmax_rows(dl.as<float>(), m, n, n, dids.as<int32_t>(), stream_);
+        FA_CUDA(cudaStreamSynchronize(stream_));
+    } else {
+        DevBuf dpl_a, dpl_w, dv, di;
+        const int tiles = tc_argmax_tiles(n);
+        dpl_a.alloc((size_t)2 * m * k * 2); dpl_w.alloc((size_t)2 * n * k * 2);
+        dv.alloc((size_t)m * tiles * 4); di.alloc((size_t)m * tiles * 4);
+        Planes pa{dpl_a.as<__nv_bfloat16>(), dpl_a.as<__nv_bfloat16>() + (size_t)m * k};
+        Planes pw{dpl_w.as<__nv_bfloat16>(), dpl_w.as<__nv_bfloat16>() + (size_t)n * k};
+        launch_split_planes(da.as<float>(), (int64_t)m * k, pa, stream_);
+        launch_split_planes(dw.as<float>(), (int64_t)n * k, pw, stream_);
+        const TcOperand oa = tc_make_operand(pa.hi, m, k, k, (int64_t)m * k, 2, kTcBlockM);
+        const TcOperand ow = tc_make_operand(pw.hi, n, k, k, (int64_t)n * k, 2, kTcBlockN);
+        Epilogue e;
+        e.bias = db.as<float>(); e.amax_val = dv.as<float>(); e.amax_idx = di.as<int32_t>();
+        launch_gemm_tc(oa, ow, m, n, k, precision == kBf16x3 ? 2 : 1, e, stream_);
+        launch_argmax_combine(dv.as<float>(), di.as<int32_t>(), m, tiles, dids.as<int32_t>(), stream_);
+        FA_CUDA(cudaStreamSynchronize(stream_));
+    }
+    FA_CUDA(cudaMemcpy(ids, dids.p, dids.bytes, cudaMemcpyDeviceToHost));
+}
+
+void Context::test_attention(const float* qkv, int batch, int frames, int heads, int dk, const int32_t* kv_len,
+                             int precision, float* out) {
+    (void)precision;
+    set_device();
+    const int d = heads * dk;
+    const size_t M = (size_t)batch * frames;
+    DevBuf dq, dout, dl;
+    dq.alloc(M * 3 * d * 4); dout.alloc(M * d * 4);
+    FA_CUDA(cudaMemcpy(dq.p, qkv, dq.bytes, cudaMemcpyHostToDevice));
+    if (kv_len) { dl.alloc((size_t)batch * 4); FA_CUDA(cudaMemcpy(dl.p, kv_len, dl.bytes, cudaMemcpyHostToDevice)); }
+    attention(dq.as<float>(), 3 * d, d, batch, frames, heads, dl.as<int>(), dout.as<float>(), Planes{}, d);
+    FA_CUDA(cudaStreamSynchronize(stream_));
+    FA_CUDA(cudaMemcpy(out, dout.p, dout.bytes, cudaMemcpyDeviceToHost));
+}
+
+}  // namespace fa

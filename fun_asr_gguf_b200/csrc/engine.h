@@ -1,0 +1,145 @@
+// Context object behind the C ABI: weights, workspace and the two graph executions
+// (encoder+adaptor, CTC head) of the reference's exported sessions.
+#pragma once
+#include "kernels.h"
+
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace fa {
+
+enum Precision { kFp32 = 0, kBf16x3 = 1, kBf16 = 2 };
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { if (p) cudaFree(p); }
+    void alloc(size_t n) {
+        if (p) { cudaFree(p); p = nullptr; }
+        bytes = n;
+        if (n) FA_CUDA(cudaMalloc(&p, n));
+    }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+struct Linear {                 // one nn.Linear: y = x W^T + b
+    const float* w = nullptr;   // [n][k] fp32
+    const float* b = nullptr;   // [n]
+    int n = 0, k = 0;
+    __nv_bfloat16* planes = nullptr;   // [2][n][k] bf16 hi|lo (tensor-core modes)
+    TcOperand op;
+};
+
+struct Act {                    // an activation matrix as the GEMMs consume it
+    const float* f32 = nullptr; // fp32 mode
+    Planes pl;                  // tensor-core modes
+    int ld = 0;
+};
+
+struct SanmLayer {
+    const float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *fsmn_w;
+    Linear qkv, out, w1, w2;
+    int d_in;
+};
+struct MhaBlock {
+    const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+    Linear qkv, out, w1, w2;    // qkv = linear_q|linear_k|linear_v stacked at load time
+};
+struct Projector {
+    Linear lin1, lin2;
+    std::vector<MhaBlock> blocks;
+    int d = 0, heads = 0;
+};
+
+class Context {
+public:
+    Context(int device, int max_batch, int64_t max_samples, int precision);
+    ~Context();
+
+    void load_tensor(const std::string& name, const float* host, const std::vector<int64_t>& shape);
+    void finalize();
+
+    // device-pointer graph executions; asynchronous on stream()
+    void encode_dev(const float* d_audio, int batch, int64_t s_phys, const int64_t* h_ilens, float* d_enc,
+                    float* d_adaptor);
+    void ctc_dev(const float* d_enc, int batch, int frames, int32_t* d_ids);
+    void collapse_dev(const int32_t* d_ids, int batch, int frames, int32_t* d_tokens, int32_t* d_starts,
+                      int32_t* d_counts);
+    // host-pointer executions (copies inside); synchronous
+    void encode_host(const float* audio, int batch, int64_t s_phys, const int64_t* ilens, float* enc, float* adaptor);
+    void ctc_host(const float* enc, int batch, int frames, int32_t* ids);
+    void front_half_host(const float* audio, int batch, int64_t s_phys, const int64_t* ilens, float* enc,
+                         float* adaptor, int32_t* ids);
+
+    void sync() { set_device(); FA_CUDA(cudaStreamSynchronize(stream_)); }
+    void set_stream(cudaStream_t s);
+    cudaStream_t stream() const { return stream_; }
+    int max_batch() const { return max_batch_; }
+    int64_t max_samples() const { return max_samples_; }
+    int precision() const { return prec_; }
+    int device() const { return device_; }
+    int vocab() const { return vocab_; }
+    void enable_taps(bool on) { taps_on_ = on; }
+    bool read_tap(const std::string& name, std::vector<float>& out, std::vector<int64_t>& shape);
+    std::vector<std::string> tap_names() const;
+
+    // kernel-level test hooks
+    void test_linear(const float* a, const float* w, const float* bias, const float* resid, int m, int n, int k,
+                     int relu, int precision, float* out, float* out_planes_sum);
+    void test_vocab_argmax(const float* a, const float* w, const float* bias, int m, int n, int k, int precision,
+                           int32_t* ids);
+    void test_attention(const float* qkv, int batch, int frames, int heads, int dk, const int32_t* kv_len,
+                        int precision, float* out);
+
+private:
+    void set_device() const { FA_CUDA(cudaSetDevice(device_)); }
+    const float* T(const std::string& name, std::vector<int64_t> shape) const;
+    Linear make_linear(const std::string& prefix, int n, int k);
+    Linear make_linear_from(const float* w, const float* b, int n, int k);
+    void build_planes(Linear& l);
+    void linear(const Act& a, const Linear& w, int m, const Epilogue& ep);
+    void attention(const float* qkv, int ld, int d_model, int batch, int frames, int heads, const int* kv_len,
+                   float* ctx_f32, Planes ctx_pl, int ldo);
+    void sanm_layer(const SanmLayer& L, bool first, int batch, int frames);
+    void projector(const Projector& P, const Act& in, int batch, int frames, const int* kv_len);
+    void tap(const char* name, const float* d, int64_t rows, int64_t cols);
+    void ensure_room(int batch, int64_t s_phys) const;
+    Act h_act(int ld) const;
+    Act ctx_act(int ld) const;
+    Act ffn_act(int ld) const;
+
+    int device_, max_batch_, prec_, vocab_ = 0;
+    int64_t max_samples_;
+    int t_mel_max_, t_max_;
+    int64_t m_max_;
+    cudaStream_t stream_ = nullptr;
+    bool own_stream_ = true, finalized_ = false, taps_on_ = false;
+
+    struct HostTensor { std::vector<int64_t> shape; std::unique_ptr<DevBuf> buf; };
+    std::map<std::string, HostTensor> tensors_;
+    std::vector<std::unique_ptr<DevBuf>> derived_;      // fused / transposed / plane copies of weights
+
+    std::vector<SanmLayer> enc_layers_;
+    const float *after_g_, *after_b_, *tp_g_, *tp_b_;
+    Projector adaptor_, ctc_;
+    Linear ctc_lo_;
+    const float *dft_t_ = nullptr, *melfb_t_ = nullptr, *pos_enc_ = nullptr;
+    int pos_rows_ = 0;
+
+    // workspace
+    DevBuf audio_, partials_, logmel_, x0_, x_, h32_, hpl_, qkv_, ctx32_, ctxpl_, ffn32_, ffnpl_, encpl_, enc_,
+        adaptor_out_, ids_, amax_val_, amax_idx_, logits_, lens_, tokens_;
+    int* d_nvalid_ = nullptr;
+    int* d_tvalid_ = nullptr;
+    int* d_tlen_ = nullptr;
+    int* h_lens_ = nullptr;      // pinned staging for the three length vectors
+    int logits_rows_ = 0;
+    std::map<std::string, std::pair<std::vector<int64_t>, std::unique_ptr<DevBuf>>> taps_;
+};
+
+}  // namespace fa

@@ -1,0 +1,432 @@
+// tcgen05 / TMEM / TMA GEMM for every dense projection on the path (SURVEY §8a rows a6, a9, a11,
+// a13, a14):  C[M][N] = A[M][K] * W[N][K]^T + bias, with ReLU / residual / bf16-plane / fused
+// vocabulary-argmax epilogues.
+//
+// Precision.  The reference computes these nn.Linear layers in fp32 and the contract is token-exact
+// CTC ids, so operands are carried as bf16 hi/lo planes (v = hi + lo, 16 mantissa bits) and each
+// K-block issues three MMA groups into the same fp32 TMEM accumulator:
+//     A_lo*W_hi + A_hi*W_lo + A_hi*W_hi          ("bf16x3", NP = 2)
+// The planes of one K-block are loaded once (4 tiles) and reused by the 3 groups, so the kernel
+// moves 4/3 of the bytes of a plain bf16 GEMM per MMA, not 2x.  NP = 1 is the plain bf16 mode.
+//
+// Structure (one CTA per SM, persistent over output tiles):
+//   warp 0      TMA producer: cp.async.bulk.tensor (3-D maps {K, rows, plane}, SWIZZLE_128B) -> smem ring
+//   warp 1      TMEM allocator + MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M128 x N256 x K16
+//   warps 2..5  epilogue: tcgen05.ld 32x32b -> registers -> bias/ReLU/residual -> global (fp32 / planes / argmax)
+// Two 256-column accumulators (all 512 TMEM columns) are ping-ponged so the epilogue of tile i
+// overlaps the main loop of tile i+1.  Pipelines: smem full/empty mbarriers (TMA <-> MMA) and
+// TMEM full/empty mbarriers (MMA <-> epilogue); tcgen05.commit signals both.
+#include "kernels.h"
+
+#include <mutex>
+
+namespace fa {
+
+namespace {
+
+constexpr int BM = kTcBlockM, BN = kTcBlockN, BK = kTcBlockK;
+constexpr int kATileBytes = BM * BK * 2;         // 16 KB
+constexpr int kWTileBytes = BN * BK * 2;         // 32 KB
+constexpr int kThreads = 192;
+constexpr int kEpiWarp0 = 2;
+constexpr uint32_t kTmemCols = 512;
+
+template <int NP> struct Cfg {
+    static constexpr int kStageBytes = NP * (kATileBytes + kWTileBytes);   // 96 KB (NP=2) / 48 KB (NP=1)
+    static constexpr int kStages = NP == 2 ? 2 : 4;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct EpiParams {
+    const float* bias;
+    const float* resid;
+    float* out;
+    __nv_bfloat16* out_hi;
+    __nv_bfloat16* out_lo;
+    float* amax_val;
+    int32_t* amax_idx;
+    int ldr, ldc, ldp, relu, n_tiles;
+};
+
+// ------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            printf("gemm_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
+                   bar, parity);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand tile in shared memory, 128-byte rows, SWIZZLE_128B: 8-row groups 1024 B apart.
+// Field layout as in cute::UMMA::SmemDescriptor (start>>4 @0, LBO>>4 @16, SBO>>4 @32, version=1 @46, layout @61).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// cute::UMMA::InstrDescriptor: D=f32 (1<<4), A=B=bf16 (1<<7, 1<<10), K-major both, N>>3 @17, M>>4 @24.
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ void tile_coords(int tile, int m_tiles, int n_tiles, int band, int& mt, int& nt) {
+    // bands of `band` m-tiles; inside a band the n index is outermost so that the CTAs running together
+    // share a handful of W tiles and one A band, both L2-resident.
+    const int per_band = band * n_tiles;
+    const int b = tile / per_band, r = tile - b * per_band;
+    const int rows = min(band, m_tiles - b * band);
+    nt = r / rows;
+    mt = b * band + (r - nt * rows);
+}
+
+template <int NP>
+__global__ void __launch_bounds__(kThreads, 1)
+k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, int m, int n, int k,
+          int band, EpiParams ep) {
+    using C = Cfg<NP>;
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t tiles_base = (raw + 1023u) & ~1023u;                      // SWIZZLE_128B wants 1024 B alignment
+    const uint32_t bars = tiles_base + C::kStages * C::kStageBytes;
+    const uint32_t bar_full = bars, bar_empty = bars + 8 * C::kStages;
+    const uint32_t bar_tfull = bars + 16 * C::kStages, bar_tempty = bar_tfull + 16;
+    const uint32_t tmem_slot = bar_tempty + 16;
+    volatile uint32_t* tmem_slot_ptr =
+        reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tiles = (m + BM - 1) / BM, n_tiles = (n + BN - 1) / BN, num_tiles = m_tiles * n_tiles;
+    const int k_blocks = (k + BK - 1) / BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C::kStages; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(bar_tfull + 8 * a, 1);
+            mbar_init(bar_tempty + 8 * a, 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                int mt, nt;
+                tile_coords(tile, m_tiles, n_tiles, band, mt, nt);
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    const uint32_t sbase = tiles_base + stage * C::kStageBytes;
+                    const uint32_t full = bar_full + 8 * stage;
+                    mbar_arrive_expect_tx(full, C::kStageBytes);
+#pragma unroll
+                    for (int p = 0; p < NP; ++p) {
+                        tma_load_3d(sbase + p * kATileBytes, &map_a, full, kb * BK, mt * BM, p);
+                        tma_load_3d(sbase + NP * kATileBytes + p * kWTileBytes, &map_w, full, kb * BK, nt * BN, p);
+                    }
+                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);       // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(bar_full + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t sbase = tiles_base + stage * C::kStageBytes;
+                    const uint32_t a_hi = sbase, a_lo = sbase + kATileBytes;
+                    const uint32_t w_hi = sbase + NP * kATileBytes, w_lo = w_hi + kWTileBytes;
+                    uint32_t accum = kb > 0 ? 1u : 0u;
+                    if constexpr (NP == 2) {
+                        // small cross terms first, the dominant hi*hi term last
+#pragma unroll
+                        for (int ks = 0; ks < BK / 16; ++ks) {
+                            tc_mma(tmem_d, umma_desc_sw128(a_lo + ks * 32), umma_desc_sw128(w_hi + ks * 32), kIdesc, accum);
+                            accum = 1u;
+                        }
+#pragma unroll
+                        for (int ks = 0; ks < BK / 16; ++ks)
+                            tc_mma(tmem_d, umma_desc_sw128(a_hi + ks * 32), umma_desc_sw128(w_lo + ks * 32), kIdesc, 1u);
+                    }
+#pragma unroll
+                    for (int ks = 0; ks < BK / 16; ++ks) {
+                        tc_mma(tmem_d, umma_desc_sw128(a_hi + ks * 32), umma_desc_sw128(w_hi + ks * 32), kIdesc, accum);
+                        accum = 1u;
+                    }
+                    tc_commit(bar_empty + 8 * stage);                 // smem stage free once these MMAs retire
+                    if (kb == k_blocks - 1) tc_commit(bar_tfull + 8 * acc);
+                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------------------------------------------ epilogue (4 warps, thread = tile row)
+        const int lane_grp = warp & 3;                               // TMEM lanes 32*lane_grp .. +31
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            int mt, nt;
+            tile_coords(tile, m_tiles, n_tiles, band, mt, nt);
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(bar_tfull + 8 * acc, acc_phase);
+            tc_fence_after();
+            const int row = mt * BM + lane_grp * 32 + lane;
+            const bool row_ok = row < m;
+            const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(lane_grp * 32) << 16);
+            float best = -INFINITY;
+            int best_i = 0x7fffffff;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t r[32];
+                tc_ld32(taddr + c * 32, r);
+                tc_wait_ld();
+                const int col0 = nt * BN + c * 32;
+                if (col0 >= n) continue;                             // warp-uniform
+                if (ep.amax_val) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int col = col0 + j;
+                        if (col < n) {
+                            const float v = __fadd_rn(__uint_as_float(r[j]), ep.bias[col]);
+                            if (v > best) { best = v; best_i = col; }
+                        }
+                    }
+                    continue;
+                }
+                if (!row_ok) continue;
+                float v[32];
+                const bool full = col0 + 32 <= n;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float x = __uint_as_float(r[j]);
+                    if (ep.bias && (full || col0 + j < n)) x = __fadd_rn(x, ep.bias[col0 + j]);
+                    if (ep.relu) x = fmaxf(x, 0.f);
+                    v[j] = x;
+                }
+                if (ep.resid) {
+                    const float* rp = ep.resid + (int64_t)row * ep.ldr + col0;
+                    if (full) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 t = *reinterpret_cast<const float4*>(rp + 4 * j);
+                            v[4 * j + 0] = __fadd_rn(t.x, v[4 * j + 0]);
+                            v[4 * j + 1] = __fadd_rn(t.y, v[4 * j + 1]);
+                            v[4 * j + 2] = __fadd_rn(t.z, v[4 * j + 2]);
+                            v[4 * j + 3] = __fadd_rn(t.w, v[4 * j + 3]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j < n) v[j] = __fadd_rn(rp[j], v[j]);
+                    }
+                }
+                if (ep.out) {
+                    float* op = ep.out + (int64_t)row * ep.ldc + col0;
+                    if (full) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            *reinterpret_cast<float4*>(op + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j < n) op[j] = v[j];
+                    }
+                }
+                if (ep.out_hi) {
+                    uint32_t hw[16], lw[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        __nv_bfloat16 h0, l0, h1, l1;
+                        split_bf16(v[2 * j], h0, l0);
+                        split_bf16(v[2 * j + 1], h1, l1);
+                        hw[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                        lw[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                    }
+                    __nv_bfloat16* hp = ep.out_hi + (int64_t)row * ep.ldp + col0;
+                    __nv_bfloat16* lp = ep.out_lo ? ep.out_lo + (int64_t)row * ep.ldp + col0 : nullptr;
+                    if (full) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            reinterpret_cast<uint4*>(hp)[j] = make_uint4(hw[4 * j], hw[4 * j + 1], hw[4 * j + 2], hw[4 * j + 3]);
+                            if (lp) reinterpret_cast<uint4*>(lp)[j] = make_uint4(lw[4 * j], lw[4 * j + 1], lw[4 * j + 2], lw[4 * j + 3]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j < n) {
+                                hp[j] = __ushort_as_bfloat16((unsigned short)((hw[j >> 1] >> ((j & 1) * 16)) & 0xffff));
+                                if (lp) lp[j] = __ushort_as_bfloat16((unsigned short)((lw[j >> 1] >> ((j & 1) * 16)) & 0xffff));
+                            }
+                    }
+                }
+            }
+            if (ep.amax_val && row_ok) {
+                ep.amax_val[(int64_t)row * ep.n_tiles + nt] = best;
+                ep.amax_idx[(int64_t)row * ep.n_tiles + nt] = best_i;
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------ host side
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+std::once_flag g_encode_once;
+int g_num_sms = 0;
+
+}  // namespace
+
+void tc_init_device() {
+    std::call_once(g_encode_once, [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        FA_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        FA_REQUIRE(fn != nullptr && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available in this driver");
+        g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    });
+    FA_CUDA(cudaFuncSetAttribute(k_gemm_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::kSmemBytes));
+    FA_CUDA(cudaFuncSetAttribute(k_gemm_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::kSmemBytes));
+    int dev = 0;
+    FA_CUDA(cudaGetDevice(&dev));
+    FA_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+}
+
+TcOperand tc_make_operand(const __nv_bfloat16* base, int rows, int k, int64_t row_stride_elems,
+                          int64_t plane_stride_elems, int planes, int box_rows) {
+    FA_REQUIRE(g_encode != nullptr, "tc_init_device() has not run");
+    FA_REQUIRE(row_stride_elems % 8 == 0 && plane_stride_elems % 8 == 0, "TMA strides must be multiples of 16 bytes");
+    FA_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base must be 16-byte aligned");
+    TcOperand op;
+    op.rows = rows; op.k = k; op.planes = planes;
+    const cuuint64_t dims[3] = {(cuuint64_t)k, (cuuint64_t)rows, (cuuint64_t)planes};
+    const cuuint64_t strides[2] = {(cuuint64_t)row_stride_elems * 2, (cuuint64_t)plane_stride_elems * 2};
+    const cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = g_encode(&op.map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(base), dims,
+                                strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw Error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+    return op;
+}
+
+int tc_argmax_tiles(int n) { return cdiv(n, BN); }
+
+void launch_gemm_tc(const TcOperand& a, const TcOperand& w, int m, int n, int k, int n_planes, const Epilogue& e,
+                    cudaStream_t st) {
+    FA_REQUIRE(a.k == k && w.k == k && a.rows >= m && w.rows == n, "tc gemm operand shapes do not match");
+    FA_REQUIRE(n_planes == 1 || n_planes == 2, "tc gemm supports 1 or 2 planes");
+    FA_REQUIRE(a.planes >= n_planes && w.planes >= n_planes, "operand lacks the requested planes");
+    EpiParams ep{};
+    ep.bias = e.bias; ep.resid = e.resid; ep.out = e.out_f32; ep.out_hi = e.out_pl.hi; ep.out_lo = e.out_pl.lo;
+    ep.amax_val = e.amax_val; ep.amax_idx = e.amax_idx;
+    ep.ldr = e.ldr; ep.ldc = e.ldc; ep.ldp = e.ldp; ep.relu = e.relu ? 1 : 0; ep.n_tiles = cdiv(n, BN);
+    FA_REQUIRE(!ep.out || (e.ldc % 4 == 0), "fp32 output stride must be a multiple of 4");
+    FA_REQUIRE(!ep.resid || (e.ldr % 4 == 0), "residual stride must be a multiple of 4");
+    FA_REQUIRE(!ep.out_hi || (e.ldp % 8 == 0), "plane output stride must be a multiple of 8");
+    FA_REQUIRE(!ep.amax_val || ep.bias, "fused argmax expects a bias");
+    const int tiles = cdiv(m, BM) * cdiv(n, BN);
+    const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+    const int band = 16;
+    if (n_planes == 2) {
+        FA_LAUNCH(k_gemm_tc<2>, grid, kThreads, Cfg<2>::kSmemBytes, st, a.map, w.map, m, n, k, band, ep);
+    } else {
+        FA_LAUNCH(k_gemm_tc<1>, grid, kThreads, Cfg<1>::kSmemBytes, st, a.map, w.map, m, n, k, band, ep);
+    }
+}
+
+}  // namespace fa

@@ -1,0 +1,262 @@
+// Bandwidth-bound row kernels: LayerNorm, FSMN memory block, length control, argmax, greedy collapse
+// (SURVEY §8a rows a5, a7, a12, a14 tail, a15).  All are one pass over their input with 128-bit
+// accesses; each row/time-strip is owned by one warp or thread so no atomics are needed.
+#include "kernels.h"
+
+namespace fa {
+
+namespace {
+
+// ------------------------------------------------------------------------------------ LayerNorm
+// model_definition.py:42-44 (eps 1e-5, encoder) and :151 (nn.LayerNorm eps 1e-12, adaptor / CTC blocks).
+// One warp per row, the row held in registers (d <= 1024).  Output as fp32 and/or bf16 hi/lo planes;
+// rows at or past t_valid[b] are written as zeros when a length vector is given (the "sweeping"
+// multiplies at model_definition.py:210,213).
+constexpr int kLnMaxVec = 8;     // float4 per lane -> d <= 1024
+
+__global__ void __launch_bounds__(256)
+k_layernorm(const float* x, int rows, int d, const float* __restrict__ gamma,
+            const float* __restrict__ beta, float eps, const int* __restrict__ t_valid, int frames,
+            float* y /* may alias x: a warp reads its whole row before it writes */,
+            __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const int nvec = d >> 2;
+    const float4* xr = reinterpret_cast<const float4*>(x + (int64_t)row * d);
+    float4 v[kLnMaxVec];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxVec; ++i) {
+        const int idx = lane + 32 * i;
+        v[i] = idx < nvec ? xr[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)d;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxVec; ++i) {
+        if (lane + 32 * i < nvec) {
+            const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
+            q += (a * a + b * b) + (c * c + e * e);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = 1.0f / sqrtf(q / (float)d + eps);
+    bool live = true;
+    if (t_valid) {
+        const int b = row / frames, t = row - b * frames;
+        live = t < t_valid[b];
+    }
+    const float4* g4 = reinterpret_cast<const float4*>(gamma);
+    const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+    for (int i = 0; i < kLnMaxVec; ++i) {
+        const int idx = lane + 32 * i;
+        if (idx >= nvec) continue;
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live) {
+            const float4 g = g4[idx], bb = b4[idx];
+            r.x = (v[i].x - mean) * rstd * g.x + bb.x;
+            r.y = (v[i].y - mean) * rstd * g.y + bb.y;
+            r.z = (v[i].z - mean) * rstd * g.z + bb.z;
+            r.w = (v[i].w - mean) * rstd * g.w + bb.w;
+        }
+        const int64_t o = (int64_t)row * d + idx * 4;
+        if (y) *reinterpret_cast<float4*>(y + o) = r;
+        if (y_hi) {
+            __nv_bfloat16 h[4], l[4];
+            split_bf16(r.x, h[0], l[0]);
+            split_bf16(r.y, h[1], l[1]);
+            split_bf16(r.z, h[2], l[2]);
+            split_bf16(r.w, h[3], l[3]);
+            *reinterpret_cast<uint2*>(y_hi + o) = *reinterpret_cast<uint2*>(h);
+            if (y_lo) *reinterpret_cast<uint2*>(y_lo + o) = *reinterpret_cast<uint2*>(l);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------ FSMN
+// MultiHeadedAttentionSANM.forward_fsmn (model_definition.py:60-66): v*m, zero-pad 5|5, depthwise
+// 11-tap correlation over time (weight (512,1,11), no bias), plus the masked input.  The residual
+// add of EncoderLayerSANM.forward (:110) is folded in (resid may alias out; layer 0 passes null, F9).
+// Thread = channel, strip of kFsmnT consecutive frames with a sliding register window.
+constexpr int kFsmnT = 32;
+
+__global__ void __launch_bounds__(kDenc)
+k_fsmn(const float* __restrict__ v, int ldv, const float* __restrict__ w, const int* __restrict__ t_valid,
+       int frames, const float* resid, float* out) {
+    const int c = threadIdx.x, b = blockIdx.y, t0 = blockIdx.x * kFsmnT;
+    const int tv = t_valid[b];
+    float wk[kFsmnK];
+#pragma unroll
+    for (int j = 0; j < kFsmnK; ++j) wk[j] = w[c * kFsmnK + j];
+    const float* vb = v + (int64_t)b * frames * ldv + c;
+    auto load = [&](int t) -> float { return (t >= 0 && t < tv) ? vb[(int64_t)t * ldv] : 0.f; };
+    float win[kFsmnK];
+#pragma unroll
+    for (int j = 0; j < kFsmnK - 1; ++j) win[j + 1] = load(t0 + j - 5);
+    for (int i = 0; i < kFsmnT; ++i) {
+        const int t = t0 + i;
+        if (t >= frames) break;
+#pragma unroll
+        for (int j = 0; j < kFsmnK - 1; ++j) win[j] = win[j + 1];
+        win[kFsmnK - 1] = load(t + 5);
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < kFsmnK; ++j) acc = fmaf(wk[j], win[j], acc);
+        float r = __fadd_rn(acc, win[5]);
+        const int64_t o = ((int64_t)b * frames + t) * kDenc + c;
+        if (resid) r = __fadd_rn(resid[o], r);
+        out[o] = r;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_row_keep(const float4* __restrict__ in, float4* __restrict__ out, int frames, int d4, const int* __restrict__ keep,
+           int64_t total4) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total4) return;
+    const int64_t row = i / d4;
+    const int b = (int)(row / frames), t = (int)(row - (int64_t)b * frames);
+    out[i] = t < keep[b] ? in[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+__global__ void __launch_bounds__(256)
+k_split_planes(const float4* __restrict__ x, int64_t n4, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float4 v = x[i];
+    __nv_bfloat16 h[4], l[4];
+    split_bf16(v.x, h[0], l[0]);
+    split_bf16(v.y, h[1], l[1]);
+    split_bf16(v.z, h[2], l[2]);
+    split_bf16(v.w, h[3], l[3]);
+    *reinterpret_cast<uint2*>(hi + i * 4) = *reinterpret_cast<uint2*>(h);
+    if (lo) *reinterpret_cast<uint2*>(lo + i * 4) = *reinterpret_cast<uint2*>(l);
+}
+
+// ------------------------------------------------------------------------------------ argmax
+// torch.argmax(..., dim=-1) returns the first index on ties (model_definition.py:337).
+__device__ __forceinline__ void amax_merge(float& bv, int& bi, float v, int i) {
+    if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+}
+
+__global__ void __launch_bounds__(256)
+k_argmax_rows(const float* __restrict__ logits, int n, int ld, int32_t* __restrict__ ids) {
+    const int row = blockIdx.x;
+    const float* p = logits + (int64_t)row * ld;
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) amax_merge(bv, bi, p[i], i);
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        amax_merge(bv, bi, ov, oi);
+    }
+    __shared__ float sv[8];
+    __shared__ int si[8];
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = bv; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; ++i) amax_merge(bv, bi, sv[i], si[i]);
+        ids[row] = bi;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_argmax_combine(const float* __restrict__ pmax, const int32_t* __restrict__ pidx, int rows, int tiles,
+                 int32_t* __restrict__ ids) {
+    // one warp per row: lanes stride over the tiles, then merge (value desc, index asc)
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int t = lane; t < tiles; t += 32) amax_merge(bv, bi, pmax[(int64_t)row * tiles + t], pidx[(int64_t)row * tiles + t]);
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        amax_merge(bv, bi, ov, oi);
+    }
+    if (lane == 0) ids[row] = bi;
+}
+
+// ------------------------------------------------------------------------------------ greedy collapse
+// decode_ctc (nano_ctc.py:70-99): merge runs, drop blanks, keep the first frame of each run.
+// One CTA per segment; block-wide exclusive scan of the "run starts here and is not blank" flags.
+__global__ void __launch_bounds__(1024)
+k_ctc_collapse(const int32_t* __restrict__ ids, int frames, int blank, int32_t* __restrict__ tokens,
+               int32_t* __restrict__ starts, int32_t* __restrict__ counts) {
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int32_t* p = ids + (int64_t)b * frames;
+    __shared__ int warp_tot[32];
+    __shared__ int base_s;
+    if (tid == 0) base_s = 0;
+    __syncthreads();
+    for (int t0 = 0; t0 < frames; t0 += 1024) {
+        const int t = t0 + tid;
+        int flag = 0, tok = 0;
+        if (t < frames) {
+            tok = p[t];
+            flag = (t == 0 || p[t - 1] != tok) && tok != blank;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, flag);
+        const int in_warp = __popc(m & ((1u << lane) - 1));
+        if (lane == 0) warp_tot[wid] = __popc(m);
+        __syncthreads();
+        int off = base_s;
+        for (int w = 0; w < wid; ++w) off += warp_tot[w];
+        if (flag) {
+            tokens[(int64_t)b * frames + off + in_warp] = tok;
+            starts[(int64_t)b * frames + off + in_warp] = t;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int s = base_s;
+            for (int w = 0; w < 32; ++w) s += warp_tot[w];
+            base_s = s;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) counts[b] = base_s;
+}
+
+}  // namespace
+
+void launch_layernorm(const float* x, int rows, int d, const float* gamma, const float* beta, float eps,
+                      const int* t_valid, int frames, float* y_f32, Planes y_pl, cudaStream_t st) {
+    FA_REQUIRE(d % 4 == 0 && d <= 128 * kLnMaxVec, "layernorm width must be a multiple of 4 and <= 1024");
+    FA_LAUNCH(k_layernorm, cdiv(rows, 8), 256, 0, st, x, rows, d, gamma, beta, eps, t_valid, frames, y_f32, y_pl.hi,
+              y_pl.lo);
+}
+
+void launch_fsmn(const float* v, int ldv, const float* w, const int* t_valid, int batch, int frames,
+                 const float* resid, float* out, cudaStream_t st) {
+    FA_LAUNCH(k_fsmn, dim3(cdiv(frames, kFsmnT), batch), kDenc, 0, st, v, ldv, w, t_valid, frames, resid, out);
+}
+
+void launch_row_keep(const float* in, float* out, int batch, int frames, int d, const int* keep, cudaStream_t st) {
+    const int64_t total4 = (int64_t)batch * frames * d / 4;
+    FA_LAUNCH(k_row_keep, cdiv(total4, 256), 256, 0, st, reinterpret_cast<const float4*>(in),
+              reinterpret_cast<float4*>(out), frames, d / 4, keep, total4);
+}
+
+void launch_split_planes(const float* x, int64_t n, Planes out, cudaStream_t st) {
+    FA_REQUIRE(n % 4 == 0, "split_planes length must be a multiple of 4");
+    FA_LAUNCH(k_split_planes, cdiv(n / 4, 256), 256, 0, st, reinterpret_cast<const float4*>(x), n / 4, out.hi, out.lo);
+}
+
+void launch_argmax_rows(const float* logits, int rows, int n, int ld, int32_t* ids, cudaStream_t st) {
+    FA_LAUNCH(k_argmax_rows, rows, 256, 0, st, logits, n, ld, ids);
+}
+
+void launch_argmax_combine(const float* pmax, const int32_t* pidx, int rows, int tiles, int32_t* ids, cudaStream_t st) {
+    FA_LAUNCH(k_argmax_combine, cdiv(rows, 8), 256, 0, st, pmax, pidx, rows, tiles, ids);
+}
+
+void launch_ctc_collapse(const int32_t* ids, int batch, int frames, int blank, int32_t* tokens, int32_t* starts,
+                         int32_t* counts, cudaStream_t st) {
+    FA_LAUNCH(k_ctc_collapse, batch, 1024, 0, st, ids, frames, blank, tokens, starts, counts);
+}
+
+}  // namespace fa

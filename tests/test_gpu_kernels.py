@@ -1,0 +1,121 @@
+"""Kernel-level parity on the B200 (through the C ABI test hooks), each against a torch fp64/fp32
+reference of the same op.  Tolerances are stated per precision mode:
+  fp32    CUDA-core fp32 FMA            : <= 2e-6 of the output range
+  bf16x3  tcgen05, hi/lo planes, 3 MMAs : <= 3e-5 of the output range (2^-16 per product)
+  bf16    tcgen05, plain bf16           : <= 2e-2 of the output range
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.gpu_util import RawContext, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 2e-6, "bf16x3": 3e-5, "bf16": 2e-2}
+
+
+@pytest.fixture(scope="module")
+def raw():
+    ctx = RawContext()
+    yield ctx
+    ctx.close()
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).numpy().astype(np.float32)
+
+
+LINEAR_SHAPES = [  # (m, n, k) — encoder qkv / out / ffn, layer-0 K=560, narrow CTC FFN, ragged M and N tiles
+    (300, 512, 512), (129, 1536, 560), (77, 128, 512), (260, 264, 128), (1, 512, 2048), (515, 2048, 512), (128, 256, 1024),
+]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "bf16"])
+@pytest.mark.parametrize("m,n,k", LINEAR_SHAPES)
+def test_linear_bias_relu_residual(raw, precision, m, n, k):
+    a, w = _rand((m, k), 1), _rand((n, k), 2, k ** -0.5)
+    bias, resid = _rand((n,), 3), _rand((m, n), 4)
+    ref = torch.from_numpy(a).double() @ torch.from_numpy(w).double().t() + torch.from_numpy(bias).double()
+    got = raw.linear(a, w, bias, precision=precision)
+    assert rel_err(got, ref) <= TOL[precision]
+    got, planes = raw.linear(a, w, bias, resid=resid, relu=True, precision=precision, planes=True)
+    ref2 = torch.relu(ref) + torch.from_numpy(resid).double()
+    assert rel_err(got, ref2) <= TOL[precision]
+    # the bf16 hi+lo planes written by the epilogue carry the same values to 16 mantissa bits
+    assert np.abs(planes - got).max() <= 2.0 ** -15 * np.abs(got).max()
+
+
+def test_bf16x3_is_much_closer_than_bf16(raw):
+    a, w, bias = _rand((256, 512), 5), _rand((512, 512), 6, 512 ** -0.5), _rand((512,), 7)
+    ref = torch.from_numpy(a).double() @ torch.from_numpy(w).double().t() + torch.from_numpy(bias).double()
+    e3, e1 = rel_err(raw.linear(a, w, bias, precision="bf16x3"), ref), rel_err(raw.linear(a, w, bias, precision="bf16"), ref)
+    assert e3 * 50 < e1
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("m,n", [(200, 5037), (131, 60515)])
+def test_vocab_argmax_never_materialises_logits(raw, precision, m, n):
+    a, w, bias = _rand((m, 512), 8), _rand((n, 512), 9, 512 ** -0.5), _rand((n,), 10, 0.1)
+    logits = torch.from_numpy(a).double() @ torch.from_numpy(w).double().t() + torch.from_numpy(bias).double()
+    top2 = logits.topk(2, -1).values
+    clear = ((top2[:, 0] - top2[:, 1]) > 1e-4).numpy()
+    ids = raw.vocab_argmax(a, w, bias, precision=precision)
+    assert ids.min() >= 0 and ids.max() < n
+    assert np.array_equal(ids[clear], logits.argmax(-1).numpy()[clear])
+
+
+def test_vocab_argmax_ties_pick_first_index(raw):
+    # identical weight rows => exactly tied logits; torch.argmax semantics = lowest index
+    a = _rand((64, 512), 11)
+    w = np.tile(_rand((1, 512), 12, 512 ** -0.5), (700, 1))
+    bias = np.zeros((700,), np.float32)
+    for precision in ("fp32", "bf16x3"):
+        assert (raw.vocab_argmax(a, w, bias, precision=precision) == 0).all()
+    bias[300] = 1.0
+    bias[650] = 1.0
+    for precision in ("fp32", "bf16x3"):
+        assert (raw.vocab_argmax(a, w, bias, precision=precision) == 300).all()
+
+
+@pytest.mark.parametrize("heads,dk", [(4, 128), (8, 128), (8, 64)])
+def test_attention_masked_keys(raw, heads, dk):
+    b, t, d = 3, 150, heads * dk
+    qkv = _rand((b * t, 3 * d), 13, 0.7)
+    kv_len = [150, 97, 1]
+    got = raw.attention(qkv, b, t, heads, dk, kv_len)
+    x = torch.from_numpy(qkv).double().view(b, t, 3, heads, dk)
+    q, k, v = (x[:, :, i].transpose(1, 2) for i in range(3))
+    s = (q * dk ** -0.5) @ k.transpose(-2, -1)
+    mask = (torch.arange(t).view(1, 1, 1, t) < torch.tensor(kv_len).view(b, 1, 1, 1)).double()
+    s = s + (mask - 1.0) * 10000.0                      # the reference's additive mask (model_definition.py:72-73)
+    ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(b * t, d)
+    assert rel_err(got, ref) <= 5e-6
+    got_full = raw.attention(qkv, b, t, heads, dk, None)   # unmasked: the CTC head's mask=None
+    ref_full = (torch.softmax((q * dk ** -0.5) @ k.transpose(-2, -1), -1) @ v).transpose(1, 2).reshape(b * t, d)
+    assert rel_err(got_full, ref_full) <= 5e-6
+
+
+@pytest.mark.parametrize("d,eps", [(512, 1e-5), (560, 1e-5), (1024, 1e-12), (512, 1e-12)])
+def test_layernorm(raw, d, eps):
+    x = _rand((333, d), 14, 3.0) + 0.5
+    g, b = _rand((d,), 15, 0.1) + 1.0, _rand((d,), 16, 0.1)
+    ref = F.layer_norm(torch.from_numpy(x).double(), (d,), torch.from_numpy(g).double(), torch.from_numpy(b).double(), eps)
+    got, planes = raw.layernorm(x, g, b, eps)
+    assert rel_err(got, ref) <= 2e-6
+    assert np.abs(planes - got).max() <= 2.0 ** -15 * np.abs(got).max()
+
+
+def test_fsmn_memory_block(raw):
+    b, t = 3, 77
+    v, w = _rand((b, t, 512), 17), _rand((512, 11), 18, 0.3)
+    resid = _rand((b, t, 512), 19)
+    tv = [77, 40, 3]
+    m = (torch.arange(t).view(1, t, 1) < torch.tensor(tv).view(b, 1, 1)).double()
+    vm = torch.from_numpy(v).double() * m
+    conv = F.conv1d(F.pad(vm.transpose(1, 2), (5, 5)), torch.from_numpy(w).double().unsqueeze(1), groups=512).transpose(1, 2)
+    ref = conv + vm
+    assert rel_err(raw.fsmn(v, w, tv), ref) <= 2e-6
+    assert rel_err(raw.fsmn(v, w, tv, resid), ref + torch.from_numpy(resid).double()) <= 2e-6

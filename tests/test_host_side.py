@@ -1,0 +1,138 @@
+"""CPU tests of the host logic: the C ABI surface, the onnxruntime-shaped shim run against the
+REAL nano_onnx.py / nano_ctc.py when the reference is mounted, and segment sharding."""
+import ctypes
+import importlib.util
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from fun_asr_gguf_b200 import _lib, ort_shim, segments, weights as Wm
+from oracle import oracle as O
+from tests import signals
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference/fun_asr_gguf"
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "funasr_b200.h")).read()
+    declared = set(re.findall(r"FA_API\s+[\w\s\*]+?\b(fa_\w+)\s*\(", header))
+    assert declared and declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.fa_abi_version() == 1
+
+
+def test_shape_helpers_match_reference_arithmetic():
+    lib = _lib.load()
+    for s in (1, 159, 160, 700, 16000, 80000, 960000, 62 * 16000, 63877):
+        assert lib.fa_frames_for_samples(s) == Wm.lfr_frames(s) == (s // 160 + 1 + 5) // 6
+        assert lib.fa_adaptor_rows_for_samples(s) == Wm.adaptor_target_len(s) == O.target_len(s)
+    assert lib.fa_frames_for_samples(960000) == 1001 and lib.fa_adaptor_rows_for_samples(960000) == 126
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful on a box without a GPU")
+def test_no_gpu_means_a_loud_error_not_a_fallback():
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    assert lib.fa_ctx_create(0, 1, 16000, 1, ctypes.byref(h)) != 0
+    assert b"cuda" in lib.fa_last_error().lower()
+    from fun_asr_gguf_b200 import FrontHalf
+    with pytest.raises(RuntimeError):
+        FrontHalf({}, device=0, max_batch=1, max_samples=16000)
+
+
+def test_segment_windows_follow_the_orchestrator():
+    sr = 16000
+    assert segments.segment_windows(62 * sr) == [(0, 62 * sr)]                 # <= segment + 2 s: one pass
+    w = segments.segment_windows(3600 * sr, 60.0, 4.0)                         # BASELINE config 4
+    assert len(w) == 65 and w[0] == (0, 60 * sr) and w[1][0] == 56 * sr
+    assert w[-1] == (3584 * sr, 3600 * sr) and all(b - a == 60 * sr for a, b in w[:-1])
+    assert Wm.lfr_frames(w[-1][1] - w[-1][0]) == 267
+    owned = [segments.shard(65, 8, r) for r in range(8)]
+    assert sorted(i for o in owned for i in o) == list(range(65)) and max(map(len, owned)) == 9
+    batches = segments.pack_batches([b - a for a, b in w], 32)
+    assert [len(b) for b in batches] == [32, 32, 1] and batches[-1] == [64]
+    audio = np.arange(3600 * sr, dtype=np.float32)
+    batch, lens = segments.pad_batch(audio, w, [64, 0])
+    assert batch.shape == (2, 60 * sr) and lens == [16 * sr, 60 * sr] and batch[0, 16 * sr:].sum() == 0
+
+
+class _OracleEngine:
+    """Stand-in for FrontHalf so the shim's session logic can run on a CPU-only box (tests only)."""
+    max_samples = 62 * 16000
+
+    def __init__(self, w, c):
+        self.w, self.c = w, c
+
+    @staticmethod
+    def frames(s):
+        return Wm.lfr_frames(s)
+
+    def encode(self, audio, ilens):
+        e, a = O.encode_batch(torch.from_numpy(audio), ilens, self.w, self.c)
+        return e.numpy(), a.numpy()
+
+    def ctc(self, enc):
+        return O.ctc_ids_batch(torch.from_numpy(enc), self.w).numpy()
+
+
+@pytest.fixture()
+def shim(monkeypatch, weights, consts):
+    eng = _OracleEngine(weights, consts)
+    monkeypatch.setattr(ort_shim, "_engine_for", lambda path, min_samples=0: eng)
+    monkeypatch.setitem(sys.modules, "onnxruntime", ort_shim)
+    return ort_shim
+
+
+def test_shim_surface(shim):
+    so = shim.SessionOptions()
+    so.add_session_config_entry("session.intra_op.allow_spinning", "0")
+    so.graph_optimization_level = shim.GraphOptimizationLevel.ORT_ENABLE_ALL
+    assert "DmlExecutionProvider" not in shim.get_available_providers()
+    enc = shim.InferenceSession("model/Fun-ASR-Nano-Encoder-Adaptor.fp32.onnx", sess_options=so, providers=["CPUExecutionProvider"])
+    ctc = shim.InferenceSession("model/Fun-ASR-Nano-CTC.fp32.onnx", sess_options=so, providers=["CPUExecutionProvider"])
+    assert [(i.name, i.type) for i in enc.get_inputs()] == [("audio", "tensor(float)"), ("ilens", "tensor(int64)")]
+    assert [o.name for o in enc.get_outputs()] == ["enc_output", "adaptor_output"]
+    assert ctc.get_inputs()[0].name == "enc_output" and "float16" not in ctc.get_inputs()[0].type
+    assert enc.get_providers()[0] == "CPUExecutionProvider"
+    audio = signals.white(16000, 0).numpy().reshape(1, 1, -1)
+    e, a = enc.run(None, {"audio": audio, "ilens": np.array([16000], np.int64)})
+    assert e.shape == (1, 17, 512) and a.shape == (1, 17, 1024) and e.dtype == np.float32
+    only = enc.run(["adaptor_output"], {"audio": audio, "ilens": np.array([16000], np.int64)})
+    assert len(only) == 1 and np.array_equal(only[0], a)
+    ids = ctc.run(None, {"enc_output": e})[0]
+    assert ids.shape == (1, 17) and ids.dtype == np.int32
+    with pytest.raises(ValueError):
+        enc.run(None, {"wave": audio})
+    with pytest.raises(ValueError):
+        ctc.run(["logits"], {"enc_output": e})
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="/root/reference not mounted")
+def test_unmodified_reference_call_sites_run_on_the_shim(shim, weights, consts):
+    """load_onnx_models / encode_audio / decode_ctc of the reference, byte-for-byte, over our sessions."""
+    def load(name):
+        spec = importlib.util.spec_from_file_location("_ref_" + name, os.path.join(REF, name + ".py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+    nano_onnx, nano_ctc = load("nano_onnx"), load("nano_ctc")
+    assert nano_onnx.onnxruntime is shim
+    enc_sess, ctc_sess, _ = nano_onnx.load_onnx_models("m/Fun-ASR-Nano-Encoder-Adaptor.fp32.onnx",
+                                                       "m/Fun-ASR-Nano-CTC.fp32.onnx", padding_secs=1)
+    sig = signals.structured(2 * 16000 + 77, 3).numpy()
+    audio_embd, enc_output = nano_onnx.encode_audio(sig, enc_sess)
+    e_o, a_o = O.encode_one(torch.from_numpy(sig), sig.shape[0], weights, consts)
+    assert audio_embd.shape == (Wm.adaptor_target_len(sig.shape[0]), 1024)
+    assert np.array_equal(enc_output[0], e_o.numpy()) and np.array_equal(audio_embd, a_o[: audio_embd.shape[0]].numpy())
+    ids = ctc_sess.run(None, {"enc_output": enc_output})[0]
+    id2token = {i: chr(0x4E00 + i % 2000) for i in range(60515)}
+    text, tokens, _ = nano_ctc.decode_ctc(ids, id2token)
+    want = O.greedy_collapse(ids[0], 60514)
+    assert [t.start for t in tokens] == [s for _, _, s in want] and len(text) == len(want)
