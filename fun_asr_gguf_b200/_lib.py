@@ -29,6 +29,8 @@ SIGNATURES = {
     "fa_ctx_sync": (C.c_int, [C.c_void_p]),
     "fa_ctx_vocab": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "fa_launch_count": (C.c_int64, []),
+    "fa_prof_begin": (C.c_int, []),
+    "fa_prof_end": (C.c_int, [C.c_char_p, C.c_int64]),
     "fa_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, c_i64_p, C.c_void_p, C.c_void_p]),
     "fa_encode_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, c_i64_p, C.c_void_p, C.c_void_p]),
     "fa_ctc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),

@@ -78,6 +78,17 @@ int fa_ctx_vocab(fa_ctx* ctx, int* vocab) { return guarded([&] { NEED(ctx); NEED
 
 int64_t fa_launch_count(void) { return fa::g_launches; }
 
+int fa_prof_begin(void) { return guarded([&] { fa::prof_begin(); }); }
+
+int fa_prof_end(char* json, int64_t capacity) {
+    return guarded([&] {
+        NEED(json);
+        const std::string s = fa::prof_end();
+        FA_REQUIRE((int64_t)s.size() + 1 <= capacity, "profile buffer too small");
+        std::memcpy(json, s.c_str(), s.size() + 1);
+    });
+}
+
 int fa_encode(fa_ctx* ctx, const float* audio, int batch, int64_t samples, const int64_t* ilens, float* enc,
               float* adaptor) {
     return guarded([&] {

@@ -178,6 +178,7 @@ void attention_init_device() {
 void launch_attention_simt(const float* q, const float* k, const float* v, int ld, int batch, int frames, int heads,
                            int dk, const int* kv_len, float* ctx_f32, Planes ctx_pl, int ldo, cudaStream_t st) {
     const dim3 grid(cdiv(frames, kQT), heads, batch);
+    prof_note_work(4.0 * batch * heads * (double)frames * frames * dk, 0.0);   // upper bound: all keys attended
     const float scale = (float)(1.0 / sqrt((double)dk));    // fp32(d_k ** -0.5), as q_h * (d_k ** -0.5) does
     if (dk == 128) {
         FA_LAUNCH(k_attention_simt<128>, grid, 256, sizeof(AttnSmem<128>), st, q, k, v, ld, frames, kv_len, ctx_f32,

@@ -37,10 +37,18 @@ inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 // Launch accounting: every kernel this library launches goes through FA_LAUNCH so that
 // bench.py can report gpu_launches from a counter instead of an estimate.
 extern thread_local int64_t g_launches;
+// Optional per-launch CUDA-event timing (bench.py's roofline leg): off by default, and when off the
+// two hooks are a single predictable branch.
+extern thread_local bool g_prof_on;
+void prof_before(const char* kernel, cudaStream_t st);
+void prof_after(cudaStream_t st);
+void prof_note_work(double flops, double bytes);   // algorithmic work of the next launch
 #define FA_LAUNCH(kernel, grid, block, smem, stream, ...)            \
     do {                                                             \
+        if (::fa::g_prof_on) ::fa::prof_before(#kernel, (stream));   \
         kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);  \
         ++::fa::g_launches;                                          \
+        if (::fa::g_prof_on) ::fa::prof_after((stream));             \
         FA_CUDA(cudaGetLastError());                                 \
     } while (0)
 

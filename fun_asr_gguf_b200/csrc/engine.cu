@@ -8,12 +8,68 @@
 #include "engine.h"
 
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstring>
 
 namespace fa {
 
 thread_local int64_t g_launches = 0;
+thread_local bool g_prof_on = false;
+
+namespace {
+struct ProfRec { std::string name; cudaEvent_t a, b; double flops, bytes; };
+thread_local std::vector<ProfRec> g_prof;
+thread_local double g_next_flops = 0.0, g_next_bytes = 0.0;
+}  // namespace
+
+void prof_note_work(double flops, double bytes) { g_next_flops = flops; g_next_bytes = bytes; }
+
+void prof_before(const char* kernel, cudaStream_t st) {
+    ProfRec r;
+    r.name = kernel;
+    const size_t lt = r.name.find('<');
+    if (lt != std::string::npos && r.name.find("k_gemm_tc") == std::string::npos) r.name = r.name.substr(0, lt);
+    r.flops = g_next_flops; r.bytes = g_next_bytes;
+    g_next_flops = g_next_bytes = 0.0;
+    FA_CUDA(cudaEventCreate(&r.a));
+    FA_CUDA(cudaEventCreate(&r.b));
+    FA_CUDA(cudaEventRecord(r.a, st));
+    g_prof.push_back(r);
+}
+
+void prof_after(cudaStream_t st) { FA_CUDA(cudaEventRecord(g_prof.back().b, st)); }
+
+void prof_begin() {
+    for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    g_prof.clear();
+    g_prof_on = true;
+}
+
+// Stops profiling and returns {"kernel": {"launches": n, "ms": total, "flops": sum, "bytes": sum}, ...} as JSON.
+std::string prof_end() {
+    g_prof_on = false;
+    std::map<std::string, std::array<double, 4>> agg;
+    for (auto& r : g_prof) {
+        FA_CUDA(cudaEventSynchronize(r.b));
+        float ms = 0.f;
+        FA_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+        auto& a = agg[r.name];
+        a[0] += 1; a[1] += ms; a[2] += r.flops; a[3] += r.bytes;
+        cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    g_prof.clear();
+    std::string out = "{";
+    bool first = true;
+    for (auto& kv : agg) {
+        char buf[512];
+        snprintf(buf, sizeof buf, "%s\"%s\": {\"launches\": %.0f, \"ms\": %.6f, \"flops\": %.6e, \"bytes\": %.6e}",
+                 first ? "" : ", ", kv.first.c_str(), kv.second[0], kv.second[1], kv.second[2], kv.second[3]);
+        out += buf;
+        first = false;
+    }
+    return out + "}";
+}
 
 namespace {
 constexpr int kLenSlots = 4;

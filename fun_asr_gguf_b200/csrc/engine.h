@@ -56,6 +56,9 @@ struct Projector {
     int d = 0, heads = 0;
 };
 
+void prof_begin();
+std::string prof_end();
+
 class Context {
 public:
     Context(int device, int max_batch, int64_t max_samples, int precision);

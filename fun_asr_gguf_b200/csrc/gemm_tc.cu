@@ -422,6 +422,7 @@ void launch_gemm_tc(const TcOperand& a, const TcOperand& w, int m, int n, int k,
     const int tiles = cdiv(m, BM) * cdiv(n, BN);
     const int grid = tiles < g_num_sms ? tiles : g_num_sms;
     const int band = 16;
+    prof_note_work(2.0 * m * (double)n * k, 0.0);
     if (n_planes == 2) {
         FA_LAUNCH(k_gemm_tc<2>, grid, kThreads, Cfg<2>::kSmemBytes, st, a.map, w.map, m, n, k, band, ep);
     } else {

@@ -175,3 +175,15 @@ def greedy_tokens(ids: np.ndarray, blank_id: int):
                 out.append((tok, i, max((i * 60 - 240) / 1000.0, 0.0)))
             prev = tok
     return out
+
+
+def profile_begin():
+    """Start per-launch CUDA-event timing of this thread's kernel launches (bench.py roofline leg)."""
+    _lib.check(_lib.load().fa_prof_begin())
+
+
+def profile_end() -> dict:
+    import json
+    buf = C.create_string_buffer(1 << 16)
+    _lib.check(_lib.load().fa_prof_end(buf, len(buf)))
+    return json.loads(buf.value.decode())

@@ -60,6 +60,10 @@ FA_API int fa_ctx_set_stream(fa_ctx* ctx, void* cuda_stream);/* run on a caller-
 FA_API int fa_ctx_sync(fa_ctx* ctx);
 FA_API int fa_ctx_vocab(fa_ctx* ctx, int* vocab);
 FA_API int64_t fa_launch_count(void);                        /* kernels launched by the calling thread so far */
+/* per-launch CUDA-event timing of the calling thread's launches, aggregated by kernel, as JSON:
+ * {"k_name": {"launches": n, "ms": total, "flops": algorithmic, "bytes": algorithmic}, ...} */
+FA_API int fa_prof_begin(void);
+FA_API int fa_prof_end(char* json_out, int64_t capacity);
 
 /* ---- encoder session: replaces encoder_sess.run / run_with_ort_values (nano_onnx.py:62,117) -------
  * audio  [batch][samples] fp32, every row zero-padded to the same physical length
