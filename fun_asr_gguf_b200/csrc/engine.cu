@@ -105,6 +105,9 @@ Context::Context(int device, int max_batch, int64_t max_samples, int precision)
     frontend_init_device();
     attention_init_device();
     tc_init_device();
+    attention_tc_init_device();
+    const char* att = getenv("FUNASR_B200_ATTENTION");     // debugging aid: "simt" keeps fp32 attention in the tensor-core modes
+    simt_attention_ = precision == kFp32 || (att && std::string(att) == "simt");
     t_mel_max_ = (int)(max_samples / kHop + 1);
     t_max_ = lfr_frames_of(max_samples);
     m_max_ = (int64_t)max_batch * t_max_;
@@ -298,6 +301,7 @@ void Context::finalize() {
     tokens_.alloc(M * 4 * 2 + (size_t)max_batch_ * 4);
     if (tc) {
         hpl_.alloc(2 * M * kDllm * 2);
+        qkvpl_.alloc(2 * M * 3 * kDllm * 2);
         ctxpl_.alloc(2 * M * kDllm * 2);
         ffnpl_.alloc(2 * M * kDffn * 2);
         encpl_.alloc(2 * M * kDenc * 2);
@@ -359,8 +363,32 @@ void Context::linear(const Act& a, const Linear& w, int m, const Epilogue& ep_in
 
 void Context::attention(const float* qkv, int ld, int d_model, int batch, int frames, int heads, const int* kv_len,
                         float* ctx_f32, Planes ctx_pl, int ldo) {
-    launch_attention_simt(qkv, qkv + d_model, qkv + 2 * d_model, ld, batch, frames, heads, d_model / heads, kv_len,
-                          ctx_f32, ctx_pl, ldo, stream_);
+    if (simt_attention_) {
+        launch_attention_simt(qkv, qkv + d_model, qkv + 2 * d_model, ld, batch, frames, heads, d_model / heads, kv_len,
+                              ctx_f32, ctx_pl, ldo, stream_);
+    } else {
+        const Planes pl = qkv_planes();
+        launch_attention_tc(pl, pl.lo - pl.hi, ld, d_model, batch, frames, heads, d_model / heads, kv_len, ctx_f32, ctx_pl,
+                            ldo, stream_);
+    }
+}
+
+Planes Context::qkv_planes() const {
+    return Planes{qkvpl_.as<__nv_bfloat16>(), qkvpl_.as<__nv_bfloat16>() + m_max_ * 3 * kDllm};
+}
+
+// Epilogue of a fused q|k|v projection: what the attention kernel in use wants to read.
+Epilogue Context::qkv_epilogue(int d_model, int heads, bool need_v_f32) const {
+    Epilogue e;
+    if (simt_attention_) {
+        e.out_f32 = qkv_.as<float>(); e.ldc = 3 * d_model;
+    } else {
+        e.out_pl = qkv_planes(); e.ldp = 3 * d_model;
+        e.pl_col_scale = (float)(1.4426950408889634 / std::sqrt((double)(d_model / heads)));   // d_k^-0.5 * log2(e)
+        e.pl_col_scale_end = d_model;
+        if (need_v_f32) { e.out_f32 = qkv_.as<float>(); e.ldc = 3 * d_model; e.f32_col_begin = 2 * d_model; }
+    }
+    return e;
 }
 
 void Context::tap(const char* name, const float* d, int64_t rows, int64_t cols) {
@@ -404,9 +432,7 @@ void Context::sanm_layer(const SanmLayer& L, bool first, int batch, int frames) 
     const Act h = h_act(L.d_in);
     launch_layernorm(xin, M, L.d_in, L.ln1_g, L.ln1_b, 1e-5f, nullptr, frames, f32 ? const_cast<float*>(h.f32) : nullptr,
                      f32 ? Planes{} : h.pl, stream_);
-    Epilogue e;
-    e.out_f32 = qkv_.as<float>(); e.ldc = 3 * kDenc;
-    linear(h, L.qkv, M, e);
+    linear(h, L.qkv, M, qkv_epilogue(kDenc, 4, true));      // fp32 v feeds the FSMN branch
     const float* qkv = qkv_.as<float>();
     // x <- (x) + fsmn(v*m): the memory branch plus, except in layer 0, the block's residual
     launch_fsmn(qkv + 2 * kDenc, 3 * kDenc, L.fsmn_w, d_tvalid_, batch, frames, first ? nullptr : x, x, stream_);
@@ -444,9 +470,7 @@ void Context::projector(const Projector& P, const Act& in, int batch, int frames
         const Act h = h_act(d);
         launch_layernorm(x, M, d, B.ln1_g, B.ln1_b, 1e-12f, nullptr, frames, f32 ? const_cast<float*>(h.f32) : nullptr,
                          f32 ? Planes{} : h.pl, stream_);
-        Epilogue eq;
-        eq.out_f32 = qkv_.as<float>(); eq.ldc = 3 * d;
-        linear(h, B.qkv, M, eq);
+        linear(h, B.qkv, M, qkv_epilogue(d, P.heads, false));
         const Act c = ctx_act(d);
         attention(qkv_.as<float>(), 3 * d, d, batch, frames, P.heads, kv_len, f32 ? const_cast<float*>(c.f32) : nullptr,
                   f32 ? Planes{} : c.pl, d);
@@ -679,15 +703,29 @@ void Context::test_vocab_argmax(const float* a, const float* w, const float* bia
 
 void Context::test_attention(const float* qkv, int batch, int frames, int heads, int dk, const int32_t* kv_len,
                              int precision, float* out) {
-    (void)precision;
     set_device();
     const int d = heads * dk;
     const size_t M = (size_t)batch * frames;
-    DevBuf dq, dout, dl;
+    DevBuf dq, dout, dl, dpl;
     dq.alloc(M * 3 * d * 4); dout.alloc(M * d * 4);
-    FA_CUDA(cudaMemcpy(dq.p, qkv, dq.bytes, cudaMemcpyHostToDevice));
     if (kv_len) { dl.alloc((size_t)batch * 4); FA_CUDA(cudaMemcpy(dl.p, kv_len, dl.bytes, cudaMemcpyHostToDevice)); }
-    attention(dq.as<float>(), 3 * d, d, batch, frames, heads, dl.as<int>(), dout.as<float>(), Planes{}, d);
+    if (precision == kFp32) {
+        FA_CUDA(cudaMemcpy(dq.p, qkv, dq.bytes, cudaMemcpyHostToDevice));
+        launch_attention_simt(dq.as<float>(), dq.as<float>() + d, dq.as<float>() + 2 * d, 3 * d, batch, frames, heads, dk,
+                              dl.as<int>(), dout.as<float>(), Planes{}, d, stream_);
+    } else {
+        // the producing GEMM would have folded d_k^-0.5 * log2(e) into the q planes; do the same here
+        std::vector<float> scaled(qkv, qkv + M * 3 * d);
+        const float s = (float)(1.4426950408889634 / std::sqrt((double)dk));
+        for (size_t r = 0; r < M; ++r)
+            for (int c = 0; c < d; ++c) scaled[r * 3 * d + c] *= s;
+        FA_CUDA(cudaMemcpy(dq.p, scaled.data(), dq.bytes, cudaMemcpyHostToDevice));
+        dpl.alloc(M * 3 * d * 2 * 2);
+        Planes pl{dpl.as<__nv_bfloat16>(), dpl.as<__nv_bfloat16>() + M * 3 * d};
+        launch_split_planes(dq.as<float>(), (int64_t)(M * 3 * d), pl, stream_);
+        launch_attention_tc(pl, (int64_t)(M * 3 * d), 3 * d, d, batch, frames, heads, dk, dl.as<int>(), dout.as<float>(),
+                            Planes{}, d, stream_);
+    }
     FA_CUDA(cudaStreamSynchronize(stream_));
     FA_CUDA(cudaMemcpy(out, dout.p, dout.bytes, cudaMemcpyDeviceToHost));
 }

@@ -112,6 +112,8 @@ private:
     void projector(const Projector& P, const Act& in, int batch, int frames, const int* kv_len);
     void tap(const char* name, const float* d, int64_t rows, int64_t cols);
     void ensure_room(int batch, int64_t s_phys) const;
+    Planes qkv_planes() const;
+    Epilogue qkv_epilogue(int d_model, int heads, bool need_v_f32) const;
     Act h_act(int ld) const;
     Act ctx_act(int ld) const;
     Act ffn_act(int ld) const;
@@ -121,7 +123,7 @@ private:
     int t_mel_max_, t_max_;
     int64_t m_max_;
     cudaStream_t stream_ = nullptr;
-    bool own_stream_ = true, finalized_ = false, taps_on_ = false;
+    bool own_stream_ = true, finalized_ = false, taps_on_ = false, simt_attention_ = true;
 
     struct HostTensor { std::vector<int64_t> shape; std::unique_ptr<DevBuf> buf; };
     std::map<std::string, HostTensor> tensors_;
@@ -135,7 +137,7 @@ private:
     int pos_rows_ = 0;
 
     // workspace
-    DevBuf audio_, partials_, logmel_, x0_, x_, h32_, hpl_, qkv_, ctx32_, ctxpl_, ffn32_, ffnpl_, encpl_, enc_,
+    DevBuf audio_, partials_, logmel_, x0_, x_, h32_, hpl_, qkv_, qkvpl_, ctx32_, ctxpl_, ffn32_, ffnpl_, encpl_, enc_,
         adaptor_out_, ids_, amax_val_, amax_idx_, logits_, lens_, tokens_;
     int* d_nvalid_ = nullptr;
     int* d_tvalid_ = nullptr;

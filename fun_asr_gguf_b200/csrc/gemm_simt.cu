@@ -84,6 +84,7 @@ void launch_gemm_simt(const float* a, int lda, const float* w, int m, int n, int
                       cudaStream_t st) {
     FA_REQUIRE(k % BK == 0 && lda % 4 == 0, "simt gemm needs K % 16 == 0 and lda % 4 == 0");
     FA_REQUIRE(ep.amax_val == nullptr, "simt gemm has no fused argmax; materialise a logits chunk instead");
+    FA_REQUIRE(ep.pl_col_scale_end == 0 && ep.f32_col_begin == 0, "simt gemm does not implement the column-range epilogue options");
     prof_note_work(2.0 * m * (double)n * k, 0.0);
     FA_LAUNCH(k_gemm_simt, dim3(cdiv(n, BN), cdiv(m, BM)), 256, 0, st, a, lda, w, m, n, k, ep.bias, ep.resid, ep.ldr,
               ep.relu ? 1 : 0, ep.out_f32, ep.ldc, ep.out_pl.hi, ep.out_pl.lo, ep.ldp);

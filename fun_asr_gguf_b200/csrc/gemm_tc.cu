@@ -17,6 +17,7 @@
 // overlaps the main loop of tile i+1.  Pipelines: smem full/empty mbarriers (TMA <-> MMA) and
 // TMEM full/empty mbarriers (MMA <-> epilogue); tcgen05.commit signals both.
 #include "kernels.h"
+#include "tc_ptx.cuh"
 
 #include <mutex>
 
@@ -46,74 +47,9 @@ struct EpiParams {
     float* amax_val;
     int32_t* amax_idx;
     int ldr, ldc, ldp, relu, n_tiles;
+    float pl_col_scale;
+    int pl_col_scale_end, f32_col_begin;
 };
-
-// ------------------------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n.reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n}\n"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) {
-            printf("gemm_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
-                   bar, parity);
-            __trap();
-        }
-    }
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-    asm volatile(
-        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-        : "memory");
-}
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major operand tile in shared memory, 128-byte rows, SWIZZLE_128B: 8-row groups 1024 B apart.
 // Field layout as in cute::UMMA::SmemDescriptor (start>>4 @0, LBO>>4 @16, SBO>>4 @32, version=1 @46, layout @61).
@@ -303,7 +239,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                             if (col0 + j < n) v[j] = __fadd_rn(rp[j], v[j]);
                     }
                 }
-                if (ep.out) {
+                if (ep.out && col0 >= ep.f32_col_begin) {
                     float* op = ep.out + (int64_t)row * ep.ldc + col0;
                     if (full) {
 #pragma unroll
@@ -317,11 +253,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                 }
                 if (ep.out_hi) {
                     uint32_t hw[16], lw[16];
+                    const float ps = col0 < ep.pl_col_scale_end ? ep.pl_col_scale : 1.0f;
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         __nv_bfloat16 h0, l0, h1, l1;
-                        split_bf16(v[2 * j], h0, l0);
-                        split_bf16(v[2 * j + 1], h1, l1);
+                        split_bf16(__fmul_rn(v[2 * j], ps), h0, l0);
+                        split_bf16(__fmul_rn(v[2 * j + 1], ps), h1, l1);
                         hw[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
                         lw[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
                     }
@@ -415,6 +352,8 @@ void launch_gemm_tc(const TcOperand& a, const TcOperand& w, int m, int n, int k,
     ep.bias = e.bias; ep.resid = e.resid; ep.out = e.out_f32; ep.out_hi = e.out_pl.hi; ep.out_lo = e.out_pl.lo;
     ep.amax_val = e.amax_val; ep.amax_idx = e.amax_idx;
     ep.ldr = e.ldr; ep.ldc = e.ldc; ep.ldp = e.ldp; ep.relu = e.relu ? 1 : 0; ep.n_tiles = cdiv(n, BN);
+    ep.pl_col_scale = e.pl_col_scale; ep.pl_col_scale_end = e.pl_col_scale_end; ep.f32_col_begin = e.f32_col_begin;
+    FA_REQUIRE(e.pl_col_scale_end % 32 == 0 && e.f32_col_begin % 32 == 0, "column ranges of the epilogue must be multiples of 32");
     FA_REQUIRE(!ep.out || (e.ldc % 4 == 0), "fp32 output stride must be a multiple of 4");
     FA_REQUIRE(!ep.resid || (e.ldr % 4 == 0), "residual stride must be a multiple of 4");
     FA_REQUIRE(!ep.out_hi || (e.ldp % 8 == 0), "plane output stride must be a multiple of 8");

@@ -9,6 +9,7 @@ namespace fa {
 // device current, once per context.
 void frontend_init_device();
 void attention_init_device();
+void attention_tc_init_device();
 void tc_init_device();
 
 // ---------------------------------------------------------------- front end (§8a a1-a4)
@@ -58,6 +59,9 @@ struct Epilogue {
     int ldc = 0;
     Planes out_pl;                   // [M][ldp] planes
     int ldp = 0;
+    float pl_col_scale = 1.f;        // plane outputs of columns < pl_col_scale_end are multiplied by this
+    int pl_col_scale_end = 0;        //   (folds d_k^-0.5 * log2 e into the q planes the attention kernel reads)
+    int f32_col_begin = 0;           // fp32 output only for columns >= this (multiple of 32)
     // fused vocabulary argmax: per (row, n-tile) partial max/idx instead of the logits
     float* amax_val = nullptr;       // [M][n_tiles]
     int32_t* amax_idx = nullptr;
@@ -82,5 +86,10 @@ int tc_argmax_tiles(int n);
 // (nullable => all `frames`).  Output ctx [B*T][ldo] fp32 and/or planes.
 void launch_attention_simt(const float* q, const float* k, const float* v, int ld, int batch, int frames, int heads,
                            int dk, const int* kv_len, float* ctx_f32, Planes ctx_pl, int ldo, cudaStream_t st);
+
+// tcgen05 attention on bf16 planes of a fused [rows][ld] q|k|v matrix (q pre-scaled by d_k^-0.5 * log2 e):
+// q at column 0, k at d_model, v at 2*d_model; head h at +h*dk.  Two planes `plane_stride` elements apart.
+void launch_attention_tc(Planes qkv, int64_t plane_stride, int ld, int d_model, int batch, int frames, int heads, int dk,
+                         const int* kv_len, float* ctx_f32, Planes ctx_pl, int ldo, cudaStream_t st);
 
 }  // namespace fa

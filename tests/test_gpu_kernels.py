@@ -80,22 +80,38 @@ def test_vocab_argmax_ties_pick_first_index(raw):
         assert (raw.vocab_argmax(a, w, bias, precision=precision) == 300).all()
 
 
-@pytest.mark.parametrize("heads,dk", [(4, 128), (8, 128), (8, 64)])
-def test_attention_masked_keys(raw, heads, dk):
-    b, t, d = 3, 150, heads * dk
+ATT_TOL = {"fp32": 5e-6, "bf16x3": 4e-5}
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("heads,dk,t", [(4, 128, 150), (8, 128, 150), (8, 64, 150), (4, 128, 1001), (8, 64, 333)])
+def test_attention_masked_keys(raw, precision, heads, dk, t):
+    b, d = 3, heads * dk
     qkv = _rand((b * t, 3 * d), 13, 0.7)
-    kv_len = [150, 97, 1]
-    got = raw.attention(qkv, b, t, heads, dk, kv_len)
+    kv_len = [t, (t * 2) // 3 + 1, 1]
+    got = raw.attention(qkv, b, t, heads, dk, kv_len, precision=precision)
     x = torch.from_numpy(qkv).double().view(b, t, 3, heads, dk)
     q, k, v = (x[:, :, i].transpose(1, 2) for i in range(3))
     s = (q * dk ** -0.5) @ k.transpose(-2, -1)
     mask = (torch.arange(t).view(1, 1, 1, t) < torch.tensor(kv_len).view(b, 1, 1, 1)).double()
     s = s + (mask - 1.0) * 10000.0                      # the reference's additive mask (model_definition.py:72-73)
     ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(b * t, d)
-    assert rel_err(got, ref) <= 5e-6
-    got_full = raw.attention(qkv, b, t, heads, dk, None)   # unmasked: the CTC head's mask=None
+    assert rel_err(got, ref) <= ATT_TOL[precision]
+    got_full = raw.attention(qkv, b, t, heads, dk, None, precision=precision)   # unmasked: the CTC head's mask=None
     ref_full = (torch.softmax((q * dk ** -0.5) @ k.transpose(-2, -1), -1) @ v).transpose(1, 2).reshape(b * t, d)
-    assert rel_err(got_full, ref_full) <= 5e-6
+    assert rel_err(got_full, ref_full) <= ATT_TOL[precision]
+
+
+def test_attention_peaked_scores(raw):
+    """Large |scores| (sharp softmax): the two-pass max must keep exp2 in range on the tensor-core path."""
+    b, t, heads, dk = 2, 200, 4, 128
+    qkv = _rand((b * t, 3 * heads * dk), 21, 1.0)
+    qkv[:, : heads * dk] *= 6.0
+    x = torch.from_numpy(qkv).double().view(b, t, 3, heads, dk)
+    q, k, v = (x[:, :, i].transpose(1, 2) for i in range(3))
+    ref = (torch.softmax((q * dk ** -0.5) @ k.transpose(-2, -1), -1) @ v).transpose(1, 2).reshape(b * t, heads * dk)
+    for precision in ("fp32", "bf16x3"):
+        assert rel_err(raw.attention(qkv, b, t, heads, dk, None, precision=precision), ref) <= 10 * ATT_TOL[precision]
 
 
 @pytest.mark.parametrize("d,eps", [(512, 1e-5), (560, 1e-5), (1024, 1e-12), (512, 1e-12)])
