@@ -46,6 +46,14 @@ template <int DK> struct ACfg {
     static constexpr uint32_t kOCol = 128;
 };
 
+// 2^x for x <= 0 on the MUFU pipe (2 ulp); denormal results flush to zero, which is what a vanishing
+// softmax weight should do.
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 struct AttnParams {
     int batch, frames, heads, d_model, ld;     // ld = row stride (elements) of the qkv planes
     const int* kv_len;
@@ -281,21 +289,20 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_sempty + 8 * sbuf);
                 const int kbase = j * KT;
+                const bool full_tile = kbase + KT <= klen;
                 uint32_t hi[32], lo[32];                             // 64 keys x bf16, packed in pairs
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                     const int half = i >> 4, w = (i & 15) * 2;       // word i covers keys 2i, 2i+1
                     const uint32_t* src = half ? s1 : s0;
-                    float p0 = exp2f(__uint_as_float(src[w]) - mx);
-                    float p1 = exp2f(__uint_as_float(src[w + 1]) - mx);
-                    if (kbase + 2 * i >= klen) p0 = 0.f;
-                    if (kbase + 2 * i + 1 >= klen) p1 = 0.f;
+                    float p0 = fast_exp2(__uint_as_float(src[w]) - mx);
+                    float p1 = fast_exp2(__uint_as_float(src[w + 1]) - mx);
+                    if (!full_tile) {
+                        if (kbase + 2 * i >= klen) p0 = 0.f;
+                        if (kbase + 2 * i + 1 >= klen) p1 = 0.f;
+                    }
                     lsum += p0 + p1;
-                    __nv_bfloat16 h0, l0, h1, l1;
-                    split_bf16(p0, h0, l0);
-                    split_bf16(p1, h1, l1);
-                    hi[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                    lo[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                    split_bf16x2(p0, p1, hi[i], lo[i]);
                 }
                 mbar_wait(bar_pempty, (p_it & 1) ^ 1);               // PV of the previous tile has consumed P
                 // row r of the K-major SWIZZLE_128B tile: 16-byte chunk c lives at chunk c ^ (r & 7)
@@ -334,13 +341,8 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                     if (p.ctx_hi) {
                         uint32_t hw[16], lw[16];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            __nv_bfloat16 h0, l0, h1, l1;
-                            split_bf16(__uint_as_float(o[2 * i]) * inv, h0, l0);
-                            split_bf16(__uint_as_float(o[2 * i + 1]) * inv, h1, l1);
-                            hw[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                            lw[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-                        }
+                        for (int i = 0; i < 16; ++i)
+                            split_bf16x2(__uint_as_float(o[2 * i]) * inv, __uint_as_float(o[2 * i + 1]) * inv, hw[i], lw[i]);
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             reinterpret_cast<uint4*>(p.ctx_hi + off)[i] = make_uint4(hw[4 * i], hw[4 * i + 1], hw[4 * i + 2], hw[4 * i + 3]);

@@ -12,7 +12,8 @@
 // Structure (one CTA per SM, persistent over output tiles):
 //   warp 0      TMA producer: cp.async.bulk.tensor (3-D maps {K, rows, plane}, SWIZZLE_128B) -> smem ring
 //   warp 1      TMEM allocator + MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M128 x N256 x K16
-//   warps 2..5  epilogue: tcgen05.ld 32x32b -> registers -> bias/ReLU/residual -> global (fp32 / planes / argmax)
+//   warps 2..9  epilogue: tcgen05.ld 32x32b -> registers -> bias/ReLU/residual -> swizzled smem transpose ->
+//               row-contiguous global stores (fp32 / bf16 planes), or a running argmax for the vocabulary
 // Two 256-column accumulators (all 512 TMEM columns) are ping-ponged so the epilogue of tile i
 // overlaps the main loop of tile i+1.  Pipelines: smem full/empty mbarriers (TMA <-> MMA) and
 // TMEM full/empty mbarriers (MMA <-> epilogue); tcgen05.commit signals both.
@@ -28,14 +29,14 @@ namespace {
 constexpr int BM = kTcBlockM, BN = kTcBlockN, BK = kTcBlockK;
 constexpr int kATileBytes = BM * BK * 2;         // 16 KB
 constexpr int kWTileBytes = BN * BK * 2;         // 32 KB
-constexpr int kThreads = 192;
-constexpr int kEpiWarp0 = 2;
+constexpr int kThreads = 320;                   // TMA warp, MMA warp, 8 epilogue warps
+constexpr int kStagingBytes = 8 * 4096;         // one 4 KB transpose tile per epilogue warp
 constexpr uint32_t kTmemCols = 512;
 
 template <int NP> struct Cfg {
     static constexpr int kStageBytes = NP * (kATileBytes + kWTileBytes);   // 96 KB (NP=2) / 48 KB (NP=1)
     static constexpr int kStages = NP == 2 ? 2 : 4;
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 struct EpiParams {
@@ -78,7 +79,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t tiles_base = (raw + 1023u) & ~1023u;                      // SWIZZLE_128B wants 1024 B alignment
-    const uint32_t bars = tiles_base + C::kStages * C::kStageBytes;
+    const uint32_t stg_base = tiles_base + C::kStages * C::kStageBytes;
+    const uint32_t bars = stg_base + kStagingBytes;
     const uint32_t bar_full = bars, bar_empty = bars + 8 * C::kStages;
     const uint32_t bar_tfull = bars + 16 * C::kStages, bar_tempty = bar_tfull + 16;
     const uint32_t tmem_slot = bar_tempty + 16;
@@ -96,7 +98,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(bar_tfull + 8 * a, 1);
-            mbar_init(bar_tempty + 8 * a, 4);
+            mbar_init(bar_tempty + 8 * a, 8);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -179,8 +181,16 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         }
         __syncwarp();
     } else {
-        // ------------------------------------------------------------------ epilogue (4 warps, thread = tile row)
-        const int lane_grp = warp & 3;                               // TMEM lanes 32*lane_grp .. +31
+        // ------------------------------------------------------------------ epilogue (8 warps)
+        // Warp e owns TMEM lanes 32*(warp&3).. (the hardware's lane-quarter rule) and column chunks
+        // 4*(e>>2) .. +3 of the 256-column accumulator.  A thread holds one row of a 32-column chunk in
+        // registers; everything that touches global memory goes through a 4 KB per-warp staging tile
+        // (XOR-swizzled, conflict-free both ways) so that loads and stores are row-contiguous:
+        // 8 lanes cover one 128-byte line instead of 32 lanes touching 32 different lines.
+        const int e = warp - 2, lane_grp = warp & 3, half = e >> 2;
+        unsigned char* stg = smem_raw + (stg_base - raw) + e * 4096;
+        const int sub = lane >> 3, q8 = lane & 7;                    // fp32 staging: row sub+4i, 16-byte chunk q8
+        const int sub4 = lane >> 2, q4 = lane & 3;                   // bf16 staging: row sub4+8i, 16-byte chunk q4
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             int mt, nt;
@@ -189,100 +199,108 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             const uint32_t acc_phase = (it >> 1) & 1;
             mbar_wait(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
-            const int row = mt * BM + lane_grp * 32 + lane;
-            const bool row_ok = row < m;
+            const int row_base = mt * BM + lane_grp * 32;
+            const int row = row_base + lane;
             const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(lane_grp * 32) << 16);
             float best = -INFINITY;
             int best_i = 0x7fffffff;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int cc = 0; cc < 4; ++cc) {
+                const int c = half * 4 + cc;
+                const int col0 = nt * BN + c * 32;
+                if (col0 >= n) break;                                // warp-uniform
+                // issue the global reads of this chunk before waiting on TMEM
+                float4 rv[8];
+                if (ep.resid) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int rr = row_base + sub + 4 * i, cq = col0 + q8 * 4;
+                        rv[i] = (rr < m && cq < n) ? *reinterpret_cast<const float4*>(ep.resid + (int64_t)rr * ep.ldr + cq)
+                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+                const float bias_l = (ep.bias && col0 + lane < n) ? ep.bias[col0 + lane] : 0.f;
                 uint32_t r[32];
                 tc_ld32(taddr + c * 32, r);
                 tc_wait_ld();
-                const int col0 = nt * BN + c * 32;
-                if (col0 >= n) continue;                             // warp-uniform
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __fadd_rn(__uint_as_float(r[j]), __shfl_sync(0xffffffffu, bias_l, j));
                 if (ep.amax_val) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int col = col0 + j;
-                        if (col < n) {
-                            const float v = __fadd_rn(__uint_as_float(r[j]), ep.bias[col]);
-                            if (v > best) { best = v; best_i = col; }
-                        }
-                    }
+                    for (int j = 0; j < 32; ++j)
+                        if (col0 + j < n && v[j] > best) { best = v[j]; best_i = col0 + j; }
                     continue;
                 }
-                if (!row_ok) continue;
-                float v[32];
-                const bool full = col0 + 32 <= n;
+                if (ep.relu) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float x = __uint_as_float(r[j]);
-                    if (ep.bias && (full || col0 + j < n)) x = __fadd_rn(x, ep.bias[col0 + j]);
-                    if (ep.relu) x = fmaxf(x, 0.f);
-                    v[j] = x;
+                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
                 }
                 if (ep.resid) {
-                    const float* rp = ep.resid + (int64_t)row * ep.ldr + col0;
-                    if (full) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 t = *reinterpret_cast<const float4*>(rp + 4 * j);
-                            v[4 * j + 0] = __fadd_rn(t.x, v[4 * j + 0]);
-                            v[4 * j + 1] = __fadd_rn(t.y, v[4 * j + 1]);
-                            v[4 * j + 2] = __fadd_rn(t.z, v[4 * j + 2]);
-                            v[4 * j + 3] = __fadd_rn(t.w, v[4 * j + 3]);
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (col0 + j < n) v[j] = __fadd_rn(rp[j], v[j]);
+                    for (int i = 0; i < 8; ++i) {
+                        const int rr = sub + 4 * i;
+                        *reinterpret_cast<float4*>(stg + rr * 128 + ((q8 ^ (rr & 7)) * 16)) = rv[i];
                     }
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 t = *reinterpret_cast<const float4*>(stg + lane * 128 + ((j ^ (lane & 7)) * 16));
+                        v[4 * j + 0] = __fadd_rn(t.x, v[4 * j + 0]);
+                        v[4 * j + 1] = __fadd_rn(t.y, v[4 * j + 1]);
+                        v[4 * j + 2] = __fadd_rn(t.z, v[4 * j + 2]);
+                        v[4 * j + 3] = __fadd_rn(t.w, v[4 * j + 3]);
+                    }
+                    __syncwarp();
                 }
                 if (ep.out && col0 >= ep.f32_col_begin) {
-                    float* op = ep.out + (int64_t)row * ep.ldc + col0;
-                    if (full) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            *reinterpret_cast<float4*>(op + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                    } else {
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<float4*>(stg + lane * 128 + ((j ^ (lane & 7)) * 16)) =
+                            make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    __syncwarp();
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (col0 + j < n) op[j] = v[j];
+                    for (int i = 0; i < 8; ++i) {
+                        const int rr = sub + 4 * i, cq = col0 + q8 * 4;
+                        const float4 t = *reinterpret_cast<const float4*>(stg + rr * 128 + ((q8 ^ (rr & 7)) * 16));
+                        if (row_base + rr < m && cq < n)
+                            *reinterpret_cast<float4*>(ep.out + (int64_t)(row_base + rr) * ep.ldc + cq) = t;
                     }
+                    __syncwarp();
                 }
                 if (ep.out_hi) {
-                    uint32_t hw[16], lw[16];
                     const float ps = col0 < ep.pl_col_scale_end ? ep.pl_col_scale : 1.0f;
+                    uint32_t hw[16], lw[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        __nv_bfloat16 h0, l0, h1, l1;
-                        split_bf16(__fmul_rn(v[2 * j], ps), h0, l0);
-                        split_bf16(__fmul_rn(v[2 * j + 1], ps), h1, l1);
-                        hw[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                        lw[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                    for (int j = 0; j < 16; ++j)
+                        split_bf16x2(__fmul_rn(v[2 * j], ps), __fmul_rn(v[2 * j + 1], ps), hw[j], lw[j]);
+                    // hi rows in the first 2 KB (64 B per row), lo rows in the second
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int o = lane * 64 + ((j ^ ((lane >> 1) & 3)) * 16);
+                        *reinterpret_cast<uint4*>(stg + o) = make_uint4(hw[4 * j], hw[4 * j + 1], hw[4 * j + 2], hw[4 * j + 3]);
+                        *reinterpret_cast<uint4*>(stg + 2048 + o) = make_uint4(lw[4 * j], lw[4 * j + 1], lw[4 * j + 2], lw[4 * j + 3]);
                     }
-                    __nv_bfloat16* hp = ep.out_hi + (int64_t)row * ep.ldp + col0;
-                    __nv_bfloat16* lp = ep.out_lo ? ep.out_lo + (int64_t)row * ep.ldp + col0 : nullptr;
-                    if (full) {
+                    __syncwarp();
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            reinterpret_cast<uint4*>(hp)[j] = make_uint4(hw[4 * j], hw[4 * j + 1], hw[4 * j + 2], hw[4 * j + 3]);
-                            if (lp) reinterpret_cast<uint4*>(lp)[j] = make_uint4(lw[4 * j], lw[4 * j + 1], lw[4 * j + 2], lw[4 * j + 3]);
+                    for (int i = 0; i < 4; ++i) {
+                        const int rr = sub4 + 8 * i, cq = col0 + q4 * 8;
+                        const int o = rr * 64 + ((q4 ^ ((rr >> 1) & 3)) * 16);
+                        if (row_base + rr < m && cq < n) {
+                            const int64_t g = (int64_t)(row_base + rr) * ep.ldp + cq;
+                            *reinterpret_cast<uint4*>(ep.out_hi + g) = *reinterpret_cast<const uint4*>(stg + o);
+                            if (ep.out_lo) *reinterpret_cast<uint4*>(ep.out_lo + g) = *reinterpret_cast<const uint4*>(stg + 2048 + o);
                         }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (col0 + j < n) {
-                                hp[j] = __ushort_as_bfloat16((unsigned short)((hw[j >> 1] >> ((j & 1) * 16)) & 0xffff));
-                                if (lp) lp[j] = __ushort_as_bfloat16((unsigned short)((lw[j >> 1] >> ((j & 1) * 16)) & 0xffff));
-                            }
                     }
+                    __syncwarp();
                 }
             }
-            if (ep.amax_val && row_ok) {
-                ep.amax_val[(int64_t)row * ep.n_tiles + nt] = best;
-                ep.amax_idx[(int64_t)row * ep.n_tiles + nt] = best_i;
+            if (ep.amax_val) {
+                // the two column halves of a row live in different warps: each writes its own partial slot
+                if (row < m) {
+                    ep.amax_val[((int64_t)row * ep.n_tiles + nt) * 2 + half] = best;
+                    ep.amax_idx[((int64_t)row * ep.n_tiles + nt) * 2 + half] = best_i;
+                }
             }
             tc_fence_before();
             __syncwarp();
@@ -341,7 +359,7 @@ TcOperand tc_make_operand(const __nv_bfloat16* base, int rows, int k, int64_t ro
     return op;
 }
 
-int tc_argmax_tiles(int n) { return cdiv(n, BN); }
+int tc_argmax_tiles(int n) { return 2 * cdiv(n, BN); }   // two column halves per 256-wide tile
 
 void launch_gemm_tc(const TcOperand& a, const TcOperand& w, int m, int n, int k, int n_planes, const Epilogue& e,
                     cudaStream_t st) {
@@ -358,6 +376,8 @@ void launch_gemm_tc(const TcOperand& a, const TcOperand& w, int m, int n, int k,
     FA_REQUIRE(!ep.resid || (e.ldr % 4 == 0), "residual stride must be a multiple of 4");
     FA_REQUIRE(!ep.out_hi || (e.ldp % 8 == 0), "plane output stride must be a multiple of 8");
     FA_REQUIRE(!ep.amax_val || ep.bias, "fused argmax expects a bias");
+    FA_REQUIRE(!ep.out || n % 4 == 0, "fp32 output needs N % 4 == 0");
+    FA_REQUIRE(!ep.out_hi || n % 8 == 0, "plane output needs N % 8 == 0");
     const int tiles = cdiv(m, BM) * cdiv(n, BN);
     const int grid = tiles < g_num_sms ? tiles : g_num_sms;
     const int band = 16;

@@ -65,13 +65,11 @@ k_layernorm(const float* x, int rows, int d, const float* __restrict__ gamma,
         const int64_t o = (int64_t)row * d + idx * 4;
         if (y) *reinterpret_cast<float4*>(y + o) = r;
         if (y_hi) {
-            __nv_bfloat16 h[4], l[4];
-            split_bf16(r.x, h[0], l[0]);
-            split_bf16(r.y, h[1], l[1]);
-            split_bf16(r.z, h[2], l[2]);
-            split_bf16(r.w, h[3], l[3]);
-            *reinterpret_cast<uint2*>(y_hi + o) = *reinterpret_cast<uint2*>(h);
-            if (y_lo) *reinterpret_cast<uint2*>(y_lo + o) = *reinterpret_cast<uint2*>(l);
+            uint2 h, l;
+            split_bf16x2(r.x, r.y, h.x, l.x);
+            split_bf16x2(r.z, r.w, h.y, l.y);
+            *reinterpret_cast<uint2*>(y_hi + o) = h;
+            if (y_lo) *reinterpret_cast<uint2*>(y_lo + o) = l;
         }
     }
 }
@@ -80,35 +78,56 @@ k_layernorm(const float* x, int rows, int d, const float* __restrict__ gamma,
 // MultiHeadedAttentionSANM.forward_fsmn (model_definition.py:60-66): v*m, zero-pad 5|5, depthwise
 // 11-tap correlation over time (weight (512,1,11), no bias), plus the masked input.  The residual
 // add of EncoderLayerSANM.forward (:110) is folded in (resid may alias out; layer 0 passes null, F9).
-// Thread = channel, strip of kFsmnT consecutive frames with a sliding register window.
-constexpr int kFsmnT = 32;
+// Thread = 4 adjacent channels (128-bit accesses), strip of kFsmnT consecutive frames; the strip's
+// kFsmnT+10 input rows and kFsmnT residual rows are all requested before any arithmetic, so each
+// thread keeps ~26 independent 16-byte loads in flight (the kernel is pure HBM streaming).
+constexpr int kFsmnT = 8;
 
-__global__ void __launch_bounds__(kDenc)
+__global__ void __launch_bounds__(kDenc / 4)
 k_fsmn(const float* __restrict__ v, int ldv, const float* __restrict__ w, const int* __restrict__ t_valid,
        int frames, const float* resid, float* out) {
-    const int c = threadIdx.x, b = blockIdx.y, t0 = blockIdx.x * kFsmnT;
+    const int c = threadIdx.x * 4, b = blockIdx.y, t0 = blockIdx.x * kFsmnT;
     const int tv = t_valid[b];
-    float wk[kFsmnK];
-#pragma unroll
-    for (int j = 0; j < kFsmnK; ++j) wk[j] = w[c * kFsmnK + j];
     const float* vb = v + (int64_t)b * frames * ldv + c;
-    auto load = [&](int t) -> float { return (t >= 0 && t < tv) ? vb[(int64_t)t * ldv] : 0.f; };
-    float win[kFsmnK];
+    float4 win[kFsmnT + kFsmnK - 1];
 #pragma unroll
-    for (int j = 0; j < kFsmnK - 1; ++j) win[j + 1] = load(t0 + j - 5);
+    for (int i = 0; i < kFsmnT + kFsmnK - 1; ++i) {
+        const int t = t0 + i - 5;
+        win[i] = (t >= 0 && t < tv) ? *reinterpret_cast<const float4*>(vb + (int64_t)t * ldv) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float4 rs[kFsmnT];
+    if (resid) {
+#pragma unroll
+        for (int i = 0; i < kFsmnT; ++i) {
+            const int t = t0 + i;
+            rs[i] = t < frames ? *reinterpret_cast<const float4*>(resid + ((int64_t)b * frames + t) * kDenc + c)
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    float wk[4][kFsmnK];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < kFsmnK; ++j) wk[i][j] = w[(c + i) * kFsmnK + j];
+#pragma unroll
     for (int i = 0; i < kFsmnT; ++i) {
         const int t = t0 + i;
         if (t >= frames) break;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int j = 0; j < kFsmnK - 1; ++j) win[j] = win[j + 1];
-        win[kFsmnK - 1] = load(t + 5);
-        float acc = 0.f;
-#pragma unroll
-        for (int j = 0; j < kFsmnK; ++j) acc = fmaf(wk[j], win[j], acc);
-        float r = __fadd_rn(acc, win[5]);
-        const int64_t o = ((int64_t)b * frames + t) * kDenc + c;
-        if (resid) r = __fadd_rn(resid[o], r);
-        out[o] = r;
+        for (int j = 0; j < kFsmnK; ++j) {
+            acc.x = fmaf(wk[0][j], win[i + j].x, acc.x);
+            acc.y = fmaf(wk[1][j], win[i + j].y, acc.y);
+            acc.z = fmaf(wk[2][j], win[i + j].z, acc.z);
+            acc.w = fmaf(wk[3][j], win[i + j].w, acc.w);
+        }
+        float4 r = make_float4(__fadd_rn(acc.x, win[i + 5].x), __fadd_rn(acc.y, win[i + 5].y),
+                               __fadd_rn(acc.z, win[i + 5].z), __fadd_rn(acc.w, win[i + 5].w));
+        if (resid) {
+            r.x = __fadd_rn(rs[i].x, r.x); r.y = __fadd_rn(rs[i].y, r.y);
+            r.z = __fadd_rn(rs[i].z, r.z); r.w = __fadd_rn(rs[i].w, r.w);
+        }
+        *reinterpret_cast<float4*>(out + ((int64_t)b * frames + t) * kDenc + c) = r;
     }
 }
 
@@ -127,13 +146,11 @@ k_split_planes(const float4* __restrict__ x, int64_t n4, __nv_bfloat16* __restri
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
     const float4 v = x[i];
-    __nv_bfloat16 h[4], l[4];
-    split_bf16(v.x, h[0], l[0]);
-    split_bf16(v.y, h[1], l[1]);
-    split_bf16(v.z, h[2], l[2]);
-    split_bf16(v.w, h[3], l[3]);
-    *reinterpret_cast<uint2*>(hi + i * 4) = *reinterpret_cast<uint2*>(h);
-    if (lo) *reinterpret_cast<uint2*>(lo + i * 4) = *reinterpret_cast<uint2*>(l);
+    uint2 h, l;
+    split_bf16x2(v.x, v.y, h.x, l.x);
+    split_bf16x2(v.z, v.w, h.y, l.y);
+    *reinterpret_cast<uint2*>(hi + i * 4) = h;
+    if (lo) *reinterpret_cast<uint2*>(lo + i * 4) = l;
 }
 
 // ------------------------------------------------------------------------------------ argmax
@@ -232,7 +249,8 @@ void launch_layernorm(const float* x, int rows, int d, const float* gamma, const
 
 void launch_fsmn(const float* v, int ldv, const float* w, const int* t_valid, int batch, int frames,
                  const float* resid, float* out, cudaStream_t st) {
-    FA_LAUNCH(k_fsmn, dim3(cdiv(frames, kFsmnT), batch), kDenc, 0, st, v, ldv, w, t_valid, frames, resid, out);
+    FA_REQUIRE(ldv % 4 == 0, "fsmn input stride must be a multiple of 4");
+    FA_LAUNCH(k_fsmn, dim3(cdiv(frames, kFsmnT), batch), kDenc / 4, 0, st, v, ldv, w, t_valid, frames, resid, out);
 }
 
 void launch_row_keep(const float* in, float* out, int batch, int frames, int d, const int* keep, cudaStream_t st) {
