@@ -17,7 +17,8 @@
 // TMEM read-modify-write of O and every dependency between a tile's softmax and the previous PV.
 //
 // One CTA per SM, persistent over (segment, head, 128-query tile) items:
-//   warp 0      TMA: Q planes once per item; K (pass 1) and K+V (pass 2) 64-key tiles into a 2-stage ring
+//   warp 0      TMA: Q planes once per item; 64-key K / V tiles into a 4-slot ring (pass 1: four K tiles in
+//               flight; pass 2: K in slots 0-1, freed as soon as S is issued, V in slots 2-3, freed after PV)
 //   warp 1      TMEM allocator + MMA issuer: S = Q K^T (M128 x N64, K-major both) into a double-buffered
 //               TMEM tile, O += P V (M128 x N d_k, P from smem K-major, V from smem MN-major: no transpose)
 //   warps 2..5  softmax: thread = query row = TMEM lane; tcgen05.ld S, max / exp2 / sum, split p into
@@ -36,12 +37,10 @@ constexpr int kAttThreads = 192;
 template <int DK> struct ACfg {
     static constexpr int kChunks = DK / 64;                 // 128-byte column chunks per head row
     static constexpr int kQBytes = 2 * kChunks * QT * 128;   // planes x chunks x rows x 128 B
-    static constexpr int kKBytes = 2 * kChunks * KT * 128;
-    static constexpr int kVBytes = kKBytes;
-    static constexpr int kStageBytes = kKBytes + kVBytes;
-    static constexpr int kStages = 2;
+    static constexpr int kKBytes = 2 * kChunks * KT * 128;   // one 64-key tile of K (or V), both planes
+    static constexpr int kSlots = 4;                         // pass 1: four K tiles in flight; pass 2: K in slots 0-1, V in 2-3
     static constexpr int kPBytes = 2 * QT * 128;             // planes x rows x (64 keys * 2 B)
-    static constexpr int kSmemBytes = kQBytes + kStages * kStageBytes + kPBytes + 1024 + 256;
+    static constexpr int kSmemBytes = kQBytes + kSlots * kKBytes + kPBytes + 1024 + 256;
     static constexpr uint32_t kTmemCols = 256;                      // S0 [0,64) | S1 [64,128) | O [128,128+DK)
     static constexpr uint32_t kOCol = 128;
 };
@@ -71,14 +70,14 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t q_base = (raw + 1023u) & ~1023u;
     const uint32_t kv_base = q_base + C::kQBytes;
-    const uint32_t p_base = kv_base + C::kStages * C::kStageBytes;
+    const uint32_t p_base = kv_base + C::kSlots * C::kKBytes;
     const uint32_t bars = p_base + C::kPBytes;
     const uint32_t bar_qfull = bars, bar_qempty = bars + 8;
-    const uint32_t bar_kvfull = bars + 16, bar_kvempty = bars + 32;       // [2] each
-    const uint32_t bar_sfull = bars + 48, bar_sempty = bars + 64;         // [2] each
-    const uint32_t bar_pfull = bars + 80, bar_pempty = bars + 88;
-    const uint32_t bar_ofull = bars + 96, bar_oempty = bars + 104;
-    const uint32_t tmem_slot = bars + 112;
+    const uint32_t bar_kvfull = bars + 16, bar_kvempty = bars + 48;       // [4] each: one pair per ring slot
+    const uint32_t bar_sfull = bars + 80, bar_sempty = bars + 96;         // [2] each
+    const uint32_t bar_pfull = bars + 112, bar_pempty = bars + 120;
+    const uint32_t bar_ofull = bars + 128, bar_oempty = bars + 136;
+    const uint32_t tmem_slot = bars + 144;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
     unsigned char* p_ptr = smem_raw + (p_base - raw);
 
@@ -88,10 +87,8 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 
     if (threadIdx.x == 0) {
         mbar_init(bar_qfull, 1); mbar_init(bar_qempty, 1);
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(bar_kvfull + 8 * s, 1); mbar_init(bar_kvempty + 8 * s, 1);
-            mbar_init(bar_sfull + 8 * s, 1);  mbar_init(bar_sempty + 8 * s, 4);
-        }
+        for (int s = 0; s < 4; ++s) { mbar_init(bar_kvfull + 8 * s, 1); mbar_init(bar_kvempty + 8 * s, 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(bar_sfull + 8 * s, 1); mbar_init(bar_sempty + 8 * s, 4); }
         mbar_init(bar_pfull, 4); mbar_init(bar_pempty, 1);
         mbar_init(bar_ofull, 1); mbar_init(bar_oempty, 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -118,7 +115,19 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     if (warp == 0) {
         // ================================================================== TMA producer
         if (lane == 0) {
-            uint32_t item_it = 0, kv_it = 0;
+            uint32_t item_it = 0, fills = 0;          // bit s of `fills`: parity of how often slot s has been filled
+            // one 64-key tile of K (which = 1) or V (which = 2), both planes, into ring slot `slot`
+            auto load_tile = [&](int slot, int which, int h, int row) {
+                mbar_wait(bar_kvempty + 8 * slot, ((fills >> slot) & 1) ^ 1);
+                const uint32_t full = bar_kvfull + 8 * slot, sb = kv_base + slot * C::kKBytes;
+                mbar_arrive_expect_tx(full, C::kKBytes);
+#pragma unroll
+                for (int pl = 0; pl < 2; ++pl)
+#pragma unroll
+                    for (int c = 0; c < C::kChunks; ++c)
+                        tma_load_3d(sb + (pl * C::kChunks + c) * KT * 128, &map_kv, full, which * p.d_model + h * DK + c * 64, row, pl);
+                fills ^= 1u << slot;
+            };
             for (int item = blockIdx.x; item < items; item += gridDim.x, ++item_it) {
                 int b, h, qt, n, klen;
                 decode(item, b, h, qt, n, klen);
@@ -131,24 +140,10 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                     for (int c = 0; c < C::kChunks; ++c)
                         tma_load_3d(q_base + (pl * C::kChunks + c) * QT * 128, &map_q, bar_qfull, h * DK + c * 64,
                                     row0 + qt * QT, pl);
-                for (int pass = 0; pass < 2; ++pass) {
-                    for (int j = 0; j < n; ++j, ++kv_it) {
-                        const uint32_t st = kv_it & 1, ph = (kv_it >> 1) & 1;
-                        mbar_wait(bar_kvempty + 8 * st, ph ^ 1);
-                        const uint32_t full = bar_kvfull + 8 * st;
-                        const uint32_t sb = kv_base + st * C::kStageBytes;
-                        mbar_arrive_expect_tx(full, pass == 0 ? C::kKBytes : C::kStageBytes);
-#pragma unroll
-                        for (int pl = 0; pl < 2; ++pl)
-#pragma unroll
-                            for (int c = 0; c < C::kChunks; ++c) {
-                                const uint32_t off = (pl * C::kChunks + c) * KT * 128;
-                                tma_load_3d(sb + off, &map_kv, full, p.d_model + h * DK + c * 64, row0 + j * KT, pl);
-                                if (pass == 1)
-                                    tma_load_3d(sb + C::kKBytes + off, &map_kv, full, 2 * p.d_model + h * DK + c * 64,
-                                                row0 + j * KT, pl);
-                            }
-                    }
+                for (int j = 0; j < n; ++j) load_tile(j & 3, 1, h, row0 + j * KT);             // pass 1: K only
+                for (int j = 0; j < n; ++j) {                                                  // pass 2: K then V
+                    load_tile(j & 1, 1, h, row0 + j * KT);
+                    load_tile(2 + (j & 1), 2, h, row0 + j * KT);
                 }
             }
         }
@@ -158,9 +153,10 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         if (lane == 0) {
             constexpr uint32_t kIdescS = umma_idesc_bf16(QT, KT, false);
             constexpr uint32_t kIdescO = umma_idesc_bf16(QT, DK, true);
-            uint32_t item_it = 0, kv_it = 0, s_it = 0, p_it = 0;
-            // S[sbuf] = Q K^T over the stage's K planes: lo*hi, hi*lo, then hi*hi
-            auto issue_s = [&](uint32_t stage_base, uint32_t sbuf) {
+            uint32_t item_it = 0, uses = 0, s_it = 0, p_it = 0;   // bit s of `uses`: parity of how often slot s has been consumed
+            // S[sbuf] = Q K^T over the K planes in `slot`: lo*hi, hi*lo, then hi*hi
+            auto issue_s = [&](int slot, uint32_t sbuf) {
+                const uint32_t stage_base = kv_base + slot * C::kKBytes;
                 const uint32_t tmem_s = tmem_base + sbuf * KT;
                 uint32_t accum = 0;
 #pragma unroll
@@ -176,47 +172,37 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                     }
                 }
             };
+            // wait for K in `slot` and a free S buffer, issue S, signal the softmax warps, free the slot
+            auto do_s = [&](int slot) {
+                const uint32_t sbuf = s_it & 1;
+                mbar_wait(bar_kvfull + 8 * slot, (uses >> slot) & 1);
+                mbar_wait(bar_sempty + 8 * sbuf, ((s_it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                issue_s(slot, sbuf);
+                tc_commit(bar_sfull + 8 * sbuf);
+                tc_commit(bar_kvempty + 8 * slot);
+                uses ^= 1u << slot;
+                ++s_it;
+            };
             for (int item = blockIdx.x; item < items; item += gridDim.x, ++item_it) {
                 int b, h, qt, n, klen;
                 decode(item, b, h, qt, n, klen);
                 mbar_wait(bar_qfull, item_it & 1);
                 tc_fence_after();
-                // ---- pass 1: row maxima
-                for (int j = 0; j < n; ++j, ++kv_it, ++s_it) {
-                    const uint32_t st = kv_it & 1, sbuf = s_it & 1;
-                    mbar_wait(bar_kvfull + 8 * st, (kv_it >> 1) & 1);
-                    mbar_wait(bar_sempty + 8 * sbuf, ((s_it >> 1) & 1) ^ 1);
-                    tc_fence_after();
-                    issue_s(kv_base + st * C::kStageBytes, sbuf);
-                    tc_commit(bar_sfull + 8 * sbuf);
-                    tc_commit(bar_kvempty + 8 * st);
-                }
-                // ---- pass 2: S one tile ahead of PV
-                {
-                    const uint32_t st = kv_it & 1, sbuf = s_it & 1;
-                    mbar_wait(bar_kvfull + 8 * st, (kv_it >> 1) & 1);
-                    mbar_wait(bar_sempty + 8 * sbuf, ((s_it >> 1) & 1) ^ 1);
-                    tc_fence_after();
-                    issue_s(kv_base + st * C::kStageBytes, sbuf);
-                    tc_commit(bar_sfull + 8 * sbuf);
-                    if (n == 1) tc_commit(bar_qempty);              // last read of Q: the next item's Q may land
-                    ++s_it;
-                }
+                for (int j = 0; j < n; ++j) do_s(j & 3);            // ---- pass 1: row maxima
+                // ---- pass 2: S runs one tile ahead of PV
+                do_s(0);
+                if (n == 1) tc_commit(bar_qempty);                  // last read of Q: the next item's Q may land
                 mbar_wait(bar_oempty, (item_it & 1) ^ 1);           // previous item's O has been read out
                 tc_fence_after();
-                for (int j = 0; j < n; ++j, ++kv_it, ++p_it) {
+                for (int j = 0; j < n; ++j, ++p_it) {
                     if (j + 1 < n) {
-                        const uint32_t nx = kv_it + 1, st = nx & 1, sbuf = s_it & 1;
-                        mbar_wait(bar_kvfull + 8 * st, (nx >> 1) & 1);
-                        mbar_wait(bar_sempty + 8 * sbuf, ((s_it >> 1) & 1) ^ 1);
-                        tc_fence_after();
-                        issue_s(kv_base + st * C::kStageBytes, sbuf);
-                        tc_commit(bar_sfull + 8 * sbuf);
+                        do_s((j + 1) & 1);
                         if (j + 2 == n) tc_commit(bar_qempty);
-                        ++s_it;
                     }
-                    const uint32_t st = kv_it & 1;
-                    const uint32_t v_base = kv_base + st * C::kStageBytes + C::kKBytes;
+                    const int vslot = 2 + (j & 1);
+                    const uint32_t v_base = kv_base + vslot * C::kKBytes;
+                    mbar_wait(bar_kvfull + 8 * vslot, (uses >> vslot) & 1);
                     mbar_wait(bar_pfull, p_it & 1);
                     tc_fence_after();
                     const uint32_t tmem_o = tmem_base + C::kOCol;
@@ -235,7 +221,8 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                         }
                     }
                     tc_commit(bar_pempty);
-                    tc_commit(bar_kvempty + 8 * st);
+                    tc_commit(bar_kvempty + 8 * vslot);
+                    uses ^= 1u << vslot;
                 }
                 tc_commit(bar_ofull);
             }
