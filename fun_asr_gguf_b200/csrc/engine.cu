@@ -168,7 +168,7 @@ void Context::build_planes(Linear& l) {
     b.alloc(2 * n * sizeof(__nv_bfloat16));
     l.planes = b.as<__nv_bfloat16>();
     launch_split_planes(l.w, n, Planes{l.planes, l.planes + n}, stream_);
-    l.op = tc_make_operand(l.planes, l.n, l.k, l.k, n, 2, kTcBlockN);
+    l.op = tc_make_weight(l.planes, l.n, l.k, n, 2);
 }
 
 Linear Context::make_linear_from(const float* w, const float* b, int n, int k) {
@@ -650,7 +650,7 @@ void Context::test_linear(const float* a, const float* w, const float* bias, con
         launch_split_planes(da.as<float>(), (int64_t)m * k, pa, stream_);
         launch_split_planes(dw.as<float>(), (int64_t)n * k, pw, stream_);
         const TcOperand oa = tc_make_operand(pa.hi, m, k, k, (int64_t)m * k, 2, kTcBlockM);
-        const TcOperand ow = tc_make_operand(pw.hi, n, k, k, (int64_t)n * k, 2, kTcBlockN);
+        const TcOperand ow = tc_make_weight(pw.hi, n, k, (int64_t)n * k, 2);
         launch_gemm_tc(oa, ow, m, n, k, precision == kBf16x3 ? 2 : 1, e, stream_);
     }
     FA_CUDA(cudaStreamSynchronize(stream_));
@@ -691,7 +691,7 @@ void Context::test_vocab_argmax(const float* a, const float* w, const float* bia
         launch_split_planes(da.as<float>(), (int64_t)m * k, pa, stream_);
         launch_split_planes(dw.as<float>(), (int64_t)n * k, pw, stream_);
         const TcOperand oa = tc_make_operand(pa.hi, m, k, k, (int64_t)m * k, 2, kTcBlockM);
-        const TcOperand ow = tc_make_operand(pw.hi, n, k, k, (int64_t)n * k, 2, kTcBlockN);
+        const TcOperand ow = tc_make_weight(pw.hi, n, k, (int64_t)n * k, 2);
         Epilogue e;
         e.bias = db.as<float>(); e.amax_val = dv.as<float>(); e.amax_idx = di.as<int32_t>();
         launch_gemm_tc(oa, ow, m, n, k, precision == kBf16x3 ? 2 : 1, e, stream_);

@@ -17,9 +17,20 @@
 // Two 256-column accumulators (all 512 TMEM columns) are ping-ponged so the epilogue of tile i
 // overlaps the main loop of tile i+1.  Pipelines: smem full/empty mbarriers (TMA <-> MMA) and
 // TMEM full/empty mbarriers (MMA <-> epilogue); tcgen05.commit signals both.
+//
+// k_gemm_tc2 is the product kernel: the same roles on a CTA PAIR (cluster of 2, tcgen05 cta_group::2).
+// A pair owns a 256 x 256 output tile; each CTA loads its own 128 rows of A and its own half
+// (128 rows) of the W tile, the leader CTA issues M256 x N256 x K16 MMAs that read both CTAs'
+// shared memory, and each CTA's TMEM receives its 128 rows of the result.  Per SM that is 64 KB per
+// K-block instead of 96 KB (less L2->SM traffic and operand fetch per MMA cycle), which also makes room
+// for a third stage.  The tail of the tile list (the last, partial wave) is cut into 128-column half
+// tiles so that a GEMM of 3.4 waves costs 3.5, not 4.  k_gemm_tc (one CTA per tile) is kept as the
+// comparison kernel (FUNASR_B200_GEMM=1cta).
 #include "kernels.h"
 #include "tc_ptx.cuh"
 
+#include <cstdlib>
+#include <cstring>
 #include <mutex>
 
 namespace fa {
@@ -39,6 +50,21 @@ template <int NP> struct Cfg {
     static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
+// CTA-pair kernel: per CTA and stage, NP planes of (A 128 x 64 + W-half up to 128 x 64)
+template <int NP> struct Cfg2 {
+    static constexpr int kHalfWBytes = (BN / 2) * BK * 2;                    // 16 KB: this CTA's 128 rows of the W tile
+    static constexpr int kStageBytes = NP * (kATileBytes + kHalfWBytes);      // 64 KB (NP=2) / 32 KB (NP=1)
+    static constexpr int kStages = NP == 2 ? 3 : 6;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// Work list of the pair kernel: `full_units` 256-column tiles, then the remaining tiles cut into
+// `1 << split_log2` column parts each (the partial last wave).
+struct Sched {
+    int m_tiles, n_tiles, band;      // in 256 x 256 pair tiles
+    int full_units, total_units, split_log2;
+};
+
 struct EpiParams {
     const float* bias;
     const float* resid;
@@ -47,7 +73,7 @@ struct EpiParams {
     __nv_bfloat16* out_lo;
     float* amax_val;
     int32_t* amax_idx;
-    int ldr, ldc, ldp, relu, n_tiles;
+    int ldr, ldc, ldp, relu, n_slots;            // n_slots: 128-column groups of N (fused argmax partials)
     float pl_col_scale;
     int pl_col_scale_end, f32_col_begin;
 };
@@ -69,6 +95,127 @@ __device__ __forceinline__ void tile_coords(int tile, int m_tiles, int n_tiles, 
     const int rows = min(band, m_tiles - b * band);
     nt = r / rows;
     mt = b * band + (r - nt * rows);
+}
+
+// Epilogue of one output unit: rows row0..row0+127 (this CTA's TMEM lanes), columns n0..n0+nw-1 held
+// in TMEM columns tmem_acc..tmem_acc+nw-1.  Run by the 8 epilogue warps of a CTA.
+// Warp e owns TMEM lanes 32*(e&3).. (the hardware's lane-quarter rule: warp id % 4) and column chunks
+// 4*(e>>2) .. +3 of the accumulator.  A thread holds one row of a 32-column chunk in registers;
+// everything that touches global memory goes through a 4 KB per-warp staging tile (XOR-swizzled,
+// conflict-free both ways) so that loads and stores are row-contiguous: 8 lanes cover one 128-byte
+// line instead of 32 lanes touching 32 different lines.
+__device__ __forceinline__ void epilogue_unit(const EpiParams& ep, unsigned char* stg, int e, int lane, int m, int n,
+                                              int row0, int n0, int nw, uint32_t tmem_acc) {
+    const int quarter = (e + 2) & 3, half = e >> 2;              // epilogue warps are warps 2..9: warp & 3 == (e + 2) & 3
+    const int sub = lane >> 3, q8 = lane & 7;                    // fp32 staging: row sub+4i, 16-byte chunk q8
+    const int sub4 = lane >> 2, q4 = lane & 3;                   // bf16 staging: row sub4+8i, 16-byte chunk q4
+    const int row_base = row0 + quarter * 32;
+    const int row = row_base + lane;
+    const uint32_t taddr = tmem_acc + ((uint32_t)(quarter * 32) << 16);
+    float best = -INFINITY;
+    int best_i = 0x7fffffff;
+    bool any = false;
+#pragma unroll 1
+    for (int cc = 0; cc < 4; ++cc) {
+        const int c = half * 4 + cc;
+        const int col0 = n0 + c * 32;
+        if (c * 32 >= nw || col0 >= n) break;                    // warp-uniform
+        any = true;
+        // issue the global reads of this chunk before waiting on TMEM
+        float4 rv[8];
+        if (ep.resid) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int rr = row_base + sub + 4 * i, cq = col0 + q8 * 4;
+                rv[i] = (rr < m && cq < n) ? *reinterpret_cast<const float4*>(ep.resid + (int64_t)rr * ep.ldr + cq)
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        const float bias_l = (ep.bias && col0 + lane < n) ? ep.bias[col0 + lane] : 0.f;
+        uint32_t r[32];
+        tc_ld32(taddr + c * 32, r);
+        tc_wait_ld();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __fadd_rn(__uint_as_float(r[j]), __shfl_sync(0xffffffffu, bias_l, j));
+        if (ep.amax_val) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (col0 + j < n && v[j] > best) { best = v[j]; best_i = col0 + j; }
+            continue;
+        }
+        if (ep.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (ep.resid) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int rr = sub + 4 * i;
+                *reinterpret_cast<float4*>(stg + rr * 128 + ((q8 ^ (rr & 7)) * 16)) = rv[i];
+            }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 t = *reinterpret_cast<const float4*>(stg + lane * 128 + ((j ^ (lane & 7)) * 16));
+                v[4 * j + 0] = __fadd_rn(t.x, v[4 * j + 0]);
+                v[4 * j + 1] = __fadd_rn(t.y, v[4 * j + 1]);
+                v[4 * j + 2] = __fadd_rn(t.z, v[4 * j + 2]);
+                v[4 * j + 3] = __fadd_rn(t.w, v[4 * j + 3]);
+            }
+            __syncwarp();
+        }
+        if (ep.out && col0 >= ep.f32_col_begin) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<float4*>(stg + lane * 128 + ((j ^ (lane & 7)) * 16)) =
+                    make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int rr = sub + 4 * i, cq = col0 + q8 * 4;
+                const float4 t = *reinterpret_cast<const float4*>(stg + rr * 128 + ((q8 ^ (rr & 7)) * 16));
+                if (row_base + rr < m && cq < n)
+                    *reinterpret_cast<float4*>(ep.out + (int64_t)(row_base + rr) * ep.ldc + cq) = t;
+            }
+            __syncwarp();
+        }
+        if (ep.out_hi) {
+            const float ps = col0 < ep.pl_col_scale_end ? ep.pl_col_scale : 1.0f;
+            uint32_t hw[16], lw[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                split_bf16x2(__fmul_rn(v[2 * j], ps), __fmul_rn(v[2 * j + 1], ps), hw[j], lw[j]);
+            // hi rows in the first 2 KB (64 B per row), lo rows in the second
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int o = lane * 64 + ((j ^ ((lane >> 1) & 3)) * 16);
+                *reinterpret_cast<uint4*>(stg + o) = make_uint4(hw[4 * j], hw[4 * j + 1], hw[4 * j + 2], hw[4 * j + 3]);
+                *reinterpret_cast<uint4*>(stg + 2048 + o) = make_uint4(lw[4 * j], lw[4 * j + 1], lw[4 * j + 2], lw[4 * j + 3]);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int rr = sub4 + 8 * i, cq = col0 + q4 * 8;
+                const int o = rr * 64 + ((q4 ^ ((rr >> 1) & 3)) * 16);
+                if (row_base + rr < m && cq < n) {
+                    const int64_t g = (int64_t)(row_base + rr) * ep.ldp + cq;
+                    *reinterpret_cast<uint4*>(ep.out_hi + g) = *reinterpret_cast<const uint4*>(stg + o);
+                    if (ep.out_lo) *reinterpret_cast<uint4*>(ep.out_lo + g) = *reinterpret_cast<const uint4*>(stg + 2048 + o);
+                }
+            }
+            __syncwarp();
+        }
+    }
+    if (ep.amax_val && any) {
+        // one partial slot per (row, 128-column group): the two column halves of a 256-wide tile live in
+        // different warps, and a half tile of the tail is exactly one group
+        if (row < m) {
+            const int slot = (n0 >> 7) + half;
+            ep.amax_val[(int64_t)row * ep.n_slots + slot] = best;
+            ep.amax_idx[(int64_t)row * ep.n_slots + slot] = best_i;
+        }
+    }
 }
 
 template <int NP>
@@ -182,15 +329,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         __syncwarp();
     } else {
         // ------------------------------------------------------------------ epilogue (8 warps)
-        // Warp e owns TMEM lanes 32*(warp&3).. (the hardware's lane-quarter rule) and column chunks
-        // 4*(e>>2) .. +3 of the 256-column accumulator.  A thread holds one row of a 32-column chunk in
-        // registers; everything that touches global memory goes through a 4 KB per-warp staging tile
-        // (XOR-swizzled, conflict-free both ways) so that loads and stores are row-contiguous:
-        // 8 lanes cover one 128-byte line instead of 32 lanes touching 32 different lines.
-        const int e = warp - 2, lane_grp = warp & 3, half = e >> 2;
+        const int e = warp - 2;
         unsigned char* stg = smem_raw + (stg_base - raw) + e * 4096;
-        const int sub = lane >> 3, q8 = lane & 7;                    // fp32 staging: row sub+4i, 16-byte chunk q8
-        const int sub4 = lane >> 2, q4 = lane & 3;                   // bf16 staging: row sub4+8i, 16-byte chunk q4
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             int mt, nt;
@@ -199,109 +339,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             const uint32_t acc_phase = (it >> 1) & 1;
             mbar_wait(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
-            const int row_base = mt * BM + lane_grp * 32;
-            const int row = row_base + lane;
-            const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(lane_grp * 32) << 16);
-            float best = -INFINITY;
-            int best_i = 0x7fffffff;
-#pragma unroll 1
-            for (int cc = 0; cc < 4; ++cc) {
-                const int c = half * 4 + cc;
-                const int col0 = nt * BN + c * 32;
-                if (col0 >= n) break;                                // warp-uniform
-                // issue the global reads of this chunk before waiting on TMEM
-                float4 rv[8];
-                if (ep.resid) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int rr = row_base + sub + 4 * i, cq = col0 + q8 * 4;
-                        rv[i] = (rr < m && cq < n) ? *reinterpret_cast<const float4*>(ep.resid + (int64_t)rr * ep.ldr + cq)
-                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                }
-                const float bias_l = (ep.bias && col0 + lane < n) ? ep.bias[col0 + lane] : 0.f;
-                uint32_t r[32];
-                tc_ld32(taddr + c * 32, r);
-                tc_wait_ld();
-                float v[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __fadd_rn(__uint_as_float(r[j]), __shfl_sync(0xffffffffu, bias_l, j));
-                if (ep.amax_val) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (col0 + j < n && v[j] > best) { best = v[j]; best_i = col0 + j; }
-                    continue;
-                }
-                if (ep.relu) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-                }
-                if (ep.resid) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int rr = sub + 4 * i;
-                        *reinterpret_cast<float4*>(stg + rr * 128 + ((q8 ^ (rr & 7)) * 16)) = rv[i];
-                    }
-                    __syncwarp();
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 t = *reinterpret_cast<const float4*>(stg + lane * 128 + ((j ^ (lane & 7)) * 16));
-                        v[4 * j + 0] = __fadd_rn(t.x, v[4 * j + 0]);
-                        v[4 * j + 1] = __fadd_rn(t.y, v[4 * j + 1]);
-                        v[4 * j + 2] = __fadd_rn(t.z, v[4 * j + 2]);
-                        v[4 * j + 3] = __fadd_rn(t.w, v[4 * j + 3]);
-                    }
-                    __syncwarp();
-                }
-                if (ep.out && col0 >= ep.f32_col_begin) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        *reinterpret_cast<float4*>(stg + lane * 128 + ((j ^ (lane & 7)) * 16)) =
-                            make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                    __syncwarp();
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int rr = sub + 4 * i, cq = col0 + q8 * 4;
-                        const float4 t = *reinterpret_cast<const float4*>(stg + rr * 128 + ((q8 ^ (rr & 7)) * 16));
-                        if (row_base + rr < m && cq < n)
-                            *reinterpret_cast<float4*>(ep.out + (int64_t)(row_base + rr) * ep.ldc + cq) = t;
-                    }
-                    __syncwarp();
-                }
-                if (ep.out_hi) {
-                    const float ps = col0 < ep.pl_col_scale_end ? ep.pl_col_scale : 1.0f;
-                    uint32_t hw[16], lw[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        split_bf16x2(__fmul_rn(v[2 * j], ps), __fmul_rn(v[2 * j + 1], ps), hw[j], lw[j]);
-                    // hi rows in the first 2 KB (64 B per row), lo rows in the second
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int o = lane * 64 + ((j ^ ((lane >> 1) & 3)) * 16);
-                        *reinterpret_cast<uint4*>(stg + o) = make_uint4(hw[4 * j], hw[4 * j + 1], hw[4 * j + 2], hw[4 * j + 3]);
-                        *reinterpret_cast<uint4*>(stg + 2048 + o) = make_uint4(lw[4 * j], lw[4 * j + 1], lw[4 * j + 2], lw[4 * j + 3]);
-                    }
-                    __syncwarp();
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int rr = sub4 + 8 * i, cq = col0 + q4 * 8;
-                        const int o = rr * 64 + ((q4 ^ ((rr >> 1) & 3)) * 16);
-                        if (row_base + rr < m && cq < n) {
-                            const int64_t g = (int64_t)(row_base + rr) * ep.ldp + cq;
-                            *reinterpret_cast<uint4*>(ep.out_hi + g) = *reinterpret_cast<const uint4*>(stg + o);
-                            if (ep.out_lo) *reinterpret_cast<uint4*>(ep.out_lo + g) = *reinterpret_cast<const uint4*>(stg + 2048 + o);
-                        }
-                    }
-                    __syncwarp();
-                }
-            }
-            if (ep.amax_val) {
-                // the two column halves of a row live in different warps: each writes its own partial slot
-                if (row < m) {
-                    ep.amax_val[((int64_t)row * ep.n_tiles + nt) * 2 + half] = best;
-                    ep.amax_idx[((int64_t)row * ep.n_tiles + nt) * 2 + half] = best_i;
-                }
-            }
+            epilogue_unit(ep, stg, e, lane, m, n, mt * BM, nt * BN, BN, tmem_base + acc * BN);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
@@ -316,6 +354,201 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     }
 }
 
+
+// ------------------------------------------------------------------------------------ CTA-pair kernel
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same offset in the pair's leader CTA (rank 0): the CTA rank within the
+// pair is bit 24 of a shared-window address (the Sm100MmaPeerBitMask convention)
+__device__ __forceinline__ uint32_t leader_addr(uint32_t a) { return a & 0xFEFFFFFFu; }
+
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tc_mma_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+// commit of the pair's MMAs: arrives on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+
+__device__ __forceinline__ void unit_coords(int u, const Sched& s, int& mt, int& n0, int& nw) {
+    int tile = u, part = 0, parts_log2 = 0;
+    if (u >= s.full_units) {
+        const int r = u - s.full_units;
+        parts_log2 = s.split_log2;
+        tile = s.full_units + (r >> parts_log2);
+        part = r & ((1 << parts_log2) - 1);
+    }
+    int nt;
+    tile_coords(tile, s.m_tiles, s.n_tiles, s.band, mt, nt);
+    nw = BN >> parts_log2;
+    n0 = nt * BN + part * nw;
+}
+
+template <int NP>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+k_gemm_tc2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, int m, int n, int k,
+           Sched sched, EpiParams ep) {
+    using C = Cfg2<NP>;
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t tiles_base = (raw + 1023u) & ~1023u;
+    const uint32_t stg_base = tiles_base + C::kStages * C::kStageBytes;
+    const uint32_t bars = stg_base + kStagingBytes;
+    const uint32_t bar_full = bars, bar_empty = bars + 8 * C::kStages;
+    const uint32_t bar_tfull = bars + 16 * C::kStages, bar_tempty = bar_tfull + 16;
+    const uint32_t tmem_slot = bar_tempty + 16;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = (int)cluster_ctarank();                 // 0 = leader (issues the MMAs), 1 = peer
+    const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+    const int k_blocks = (k + BK - 1) / BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C::kStages; ++s) {
+            mbar_init(bar_full + 8 * s, 1);       // used in the leader only: one arrive.expect_tx for both CTAs' bytes
+            mbar_init(bar_empty + 8 * s, 1);      // one multicast commit per use, in each CTA
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(bar_tfull + 8 * a, 1);      // multicast commit, in each CTA
+            mbar_init(bar_tempty + 8 * a, 16);    // used in the leader only: 8 epilogue warps of each CTA
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();                           // both CTAs' barriers initialised, both TMEM allocations done
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer (both CTAs)
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int u = pair; u < sched.total_units; u += num_pairs) {
+                int mt, n0, nw;
+                unit_coords(u, sched, mt, n0, nw);
+                const int w_rows = nw >> 1;                               // this CTA's share of the W tile
+                const int a_row = (mt * 2 + rank) * BM, w_row = n0 + rank * w_rows;
+                const uint32_t cta_bytes = NP * (kATileBytes + w_rows * BK * 2);
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    const uint32_t sbase = tiles_base + stage * C::kStageBytes;
+                    const uint32_t full = leader_addr(bar_full + 8 * stage);
+                    if (rank == 0) mbar_arrive_expect_tx(bar_full + 8 * stage, 2 * cta_bytes);
+#pragma unroll
+                    for (int p = 0; p < NP; ++p) {
+                        tma_load_3d_pair(sbase + p * kATileBytes, &map_a, full, kb * BK, a_row, p);
+                        const uint32_t wdst = sbase + NP * kATileBytes + p * C::kHalfWBytes;
+                        for (int r = 0; r < w_rows; r += 64)
+                            tma_load_3d_pair(wdst + r * BK * 2, &map_w, full, kb * BK, w_row + r, p);
+                    }
+                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+        if (rank == 0 && lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int u = pair; u < sched.total_units; u += num_pairs, ++it) {
+                int mt, n0, nw;
+                unit_coords(u, sched, mt, n0, nw);
+                // D = f32, A = B = bf16, K-major both, N = nw, M = 256 (128 rows in each CTA)
+                const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(nw >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);       // both CTAs' epilogues have drained this accumulator
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(bar_full + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t sbase = tiles_base + stage * C::kStageBytes;
+                    const uint32_t a_hi = sbase, a_lo = sbase + kATileBytes;
+                    const uint32_t w_hi = sbase + NP * kATileBytes, w_lo = w_hi + C::kHalfWBytes;
+                    uint32_t accum = kb > 0 ? 1u : 0u;
+                    if constexpr (NP == 2) {
+#pragma unroll
+                        for (int ks = 0; ks < BK / 16; ++ks) {
+                            tc_mma_pair(tmem_d, umma_desc_sw128(a_lo + ks * 32), umma_desc_sw128(w_hi + ks * 32), idesc, accum);
+                            accum = 1u;
+                        }
+#pragma unroll
+                        for (int ks = 0; ks < BK / 16; ++ks)
+                            tc_mma_pair(tmem_d, umma_desc_sw128(a_hi + ks * 32), umma_desc_sw128(w_lo + ks * 32), idesc, 1u);
+                    }
+#pragma unroll
+                    for (int ks = 0; ks < BK / 16; ++ks) {
+                        tc_mma_pair(tmem_d, umma_desc_sw128(a_hi + ks * 32), umma_desc_sw128(w_hi + ks * 32), idesc, accum);
+                        accum = 1u;
+                    }
+                    tc_commit_pair(bar_empty + 8 * stage);            // frees this stage in both CTAs
+                    if (kb == k_blocks - 1) tc_commit_pair(bar_tfull + 8 * acc);
+                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------------------------------------------ epilogue (8 warps in each CTA)
+        const int e = warp - 2;
+        unsigned char* stg = smem_raw + (stg_base - raw) + e * 4096;
+        int it = 0;
+        for (int u = pair; u < sched.total_units; u += num_pairs, ++it) {
+            int mt, n0, nw;
+            unit_coords(u, sched, mt, n0, nw);
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(bar_tfull + 8 * acc, acc_phase);
+            tc_fence_after();
+            epilogue_unit(ep, stg, e, lane, m, n, (mt * 2 + rank) * BM, n0, nw, tmem_base + acc * BN);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(leader_addr(bar_tempty + 8 * acc));
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();                           // the peer's smem and TMEM stay alive until the leader's last MMA retired
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------------------------ host side
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -323,6 +556,7 @@ using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
 EncodeTiledFn g_encode = nullptr;
 std::once_flag g_encode_once;
 int g_num_sms = 0;
+int g_num_pairs = 0;      // CTA pairs (clusters of 2) that can be co-resident with the pair kernel's footprint
 
 }  // namespace
 
@@ -336,9 +570,22 @@ void tc_init_device() {
     });
     FA_CUDA(cudaFuncSetAttribute(k_gemm_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::kSmemBytes));
     FA_CUDA(cudaFuncSetAttribute(k_gemm_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::kSmemBytes));
+    FA_CUDA(cudaFuncSetAttribute(k_gemm_tc2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<1>::kSmemBytes));
+    FA_CUDA(cudaFuncSetAttribute(k_gemm_tc2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<2>::kSmemBytes));
     int dev = 0;
     FA_CUDA(cudaGetDevice(&dev));
     FA_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+    // how many clusters of 2 fit at once (one CTA per SM by shared memory): 74 on a full B200
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(g_num_sms & ~1)); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = Cfg2<2>::kSmemBytes;
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeClusterDimension;
+    at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+    cfg.attrs = &at; cfg.numAttrs = 1;
+    int clusters = 0;
+    FA_CUDA(cudaOccupancyMaxActiveClusters(&clusters, k_gemm_tc2<2>, &cfg));
+    g_num_pairs = clusters < g_num_sms / 2 ? clusters : g_num_sms / 2;
+    FA_REQUIRE(g_num_pairs >= 1, "no CTA pair of the tcgen05 GEMM fits on this device");
 }
 
 TcOperand tc_make_operand(const __nv_bfloat16* base, int rows, int k, int64_t row_stride_elems,
@@ -359,7 +606,26 @@ TcOperand tc_make_operand(const __nv_bfloat16* base, int rows, int k, int64_t ro
     return op;
 }
 
-int tc_argmax_tiles(int n) { return 2 * cdiv(n, BN); }   // two column halves per 256-wide tile
+TcOperand tc_make_weight(const __nv_bfloat16* base, int rows, int k, int64_t plane_stride_elems, int planes) {
+    TcOperand op = tc_make_operand(base, rows, k, k, plane_stride_elems, planes, BN);
+    op.map64 = tc_make_operand(base, rows, k, k, plane_stride_elems, planes, 64).map;
+    op.has64 = true;
+    return op;
+}
+
+int tc_argmax_tiles(int n) { return 2 * cdiv(n, BN); }   // one partial slot per 128 columns
+
+namespace {
+// 0 = choose by size, 1 = one CTA per tile, 2 = CTA pairs.  FUNASR_B200_GEMM=1cta|2cta is a test and
+// comparison aid; read at every launch so a test can flip it.
+int gemm_kernel_override() {
+    const char* s = getenv("FUNASR_B200_GEMM");
+    if (!s) return 0;
+    if (!strcmp(s, "1cta")) return 1;
+    if (!strcmp(s, "2cta")) return 2;
+    return 0;
+}
+}  // namespace
 
 void launch_gemm_tc(const TcOperand& a, const TcOperand& w, int m, int n, int k, int n_planes, const Epilogue& e,
                     cudaStream_t st) {
@@ -369,7 +635,7 @@ void launch_gemm_tc(const TcOperand& a, const TcOperand& w, int m, int n, int k,
     EpiParams ep{};
     ep.bias = e.bias; ep.resid = e.resid; ep.out = e.out_f32; ep.out_hi = e.out_pl.hi; ep.out_lo = e.out_pl.lo;
     ep.amax_val = e.amax_val; ep.amax_idx = e.amax_idx;
-    ep.ldr = e.ldr; ep.ldc = e.ldc; ep.ldp = e.ldp; ep.relu = e.relu ? 1 : 0; ep.n_tiles = cdiv(n, BN);
+    ep.ldr = e.ldr; ep.ldc = e.ldc; ep.ldp = e.ldp; ep.relu = e.relu ? 1 : 0; ep.n_slots = tc_argmax_tiles(n);
     ep.pl_col_scale = e.pl_col_scale; ep.pl_col_scale_end = e.pl_col_scale_end; ep.f32_col_begin = e.f32_col_begin;
     FA_REQUIRE(e.pl_col_scale_end % 32 == 0 && e.f32_col_begin % 32 == 0, "column ranges of the epilogue must be multiples of 32");
     FA_REQUIRE(!ep.out || (e.ldc % 4 == 0), "fp32 output stride must be a multiple of 4");
@@ -378,10 +644,29 @@ void launch_gemm_tc(const TcOperand& a, const TcOperand& w, int m, int n, int k,
     FA_REQUIRE(!ep.amax_val || ep.bias, "fused argmax expects a bias");
     FA_REQUIRE(!ep.out || n % 4 == 0, "fp32 output needs N % 4 == 0");
     FA_REQUIRE(!ep.out_hi || n % 8 == 0, "plane output needs N % 8 == 0");
+    prof_note_work(2.0 * m * (double)n * k, 0.0);
+    // CTA pairs (256 x 256 tiles) once there is at least a full wave of them; below that the 128-row
+    // tiles of the single-CTA kernel spread a small M over twice as many SMs.
+    const int pair_tiles = cdiv(m, 2 * BM) * cdiv(n, BN);
+    const int force = gemm_kernel_override();
+    if (w.has64 && force != 1 && (force == 2 || pair_tiles >= g_num_pairs)) {
+        Sched s{};
+        s.m_tiles = cdiv(m, 2 * BM); s.n_tiles = cdiv(n, BN); s.band = 8;
+        const int pairs = pair_tiles < g_num_pairs ? pair_tiles : g_num_pairs;
+        s.full_units = pair_tiles / pairs * pairs;
+        const int rest = pair_tiles - s.full_units;
+        s.split_log2 = (rest > 0 && 2 * rest <= pairs) ? 1 : 0;      // a last wave at most half full is cut into half tiles
+        s.total_units = s.full_units + (rest << s.split_log2);
+        if (n_planes == 2) {
+            FA_LAUNCH(k_gemm_tc2<2>, 2 * pairs, kThreads, Cfg2<2>::kSmemBytes, st, a.map, w.map64, m, n, k, s, ep);
+        } else {
+            FA_LAUNCH(k_gemm_tc2<1>, 2 * pairs, kThreads, Cfg2<1>::kSmemBytes, st, a.map, w.map64, m, n, k, s, ep);
+        }
+        return;
+    }
     const int tiles = cdiv(m, BM) * cdiv(n, BN);
     const int grid = tiles < g_num_sms ? tiles : g_num_sms;
     const int band = 16;
-    prof_note_work(2.0 * m * (double)n * k, 0.0);
     if (n_planes == 2) {
         FA_LAUNCH(k_gemm_tc<2>, grid, kThreads, Cfg<2>::kSmemBytes, st, a.map, w.map, m, n, k, band, ep);
     } else {

@@ -73,9 +73,13 @@ void launch_gemm_simt(const float* a, int lda, const float* w, int m, int n, int
 struct TcOperand {
     CUtensorMap map;        // 3D: {K, rows, planes}, box {64, box_rows, 1}, SWIZZLE_128B
     int rows = 0, k = 0, planes = 0;
+    CUtensorMap map64;      // weights only: the same tensor with 64-row boxes (CTA-pair kernel)
+    bool has64 = false;
 };
 TcOperand tc_make_operand(const __nv_bfloat16* base, int rows, int k, int64_t row_stride_elems, int64_t plane_stride_elems,
                           int planes, int box_rows);
+// a weight matrix [planes][rows][k], contiguous rows: both box shapes, so either GEMM kernel can read it
+TcOperand tc_make_weight(const __nv_bfloat16* base, int rows, int k, int64_t plane_stride_elems, int planes);
 constexpr int kTcBlockM = 128, kTcBlockN = 256, kTcBlockK = 64;
 void launch_gemm_tc(const TcOperand& a, const TcOperand& w, int m, int n, int k, int n_planes, const Epilogue& ep,
                     cudaStream_t st);

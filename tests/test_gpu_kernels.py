@@ -33,9 +33,18 @@ LINEAR_SHAPES = [  # (m, n, k) — encoder qkv / out / ffn, layer-0 K=560, narro
 ]
 
 
+@pytest.fixture(params=["1cta", "2cta"])
+def gemm_kernel(request, monkeypatch):
+    """Force the single-CTA or the CTA-pair tcgen05 GEMM (the library picks by size otherwise)."""
+    monkeypatch.setenv("FUNASR_B200_GEMM", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("precision", ["fp32", "bf16x3", "bf16"])
 @pytest.mark.parametrize("m,n,k", LINEAR_SHAPES)
-def test_linear_bias_relu_residual(raw, precision, m, n, k):
+def test_linear_bias_relu_residual(raw, gemm_kernel, precision, m, n, k):
+    if precision == "fp32" and gemm_kernel == "2cta":
+        pytest.skip("fp32 mode does not use the tensor-core kernels")
     a, w = _rand((m, k), 1), _rand((n, k), 2, k ** -0.5)
     bias, resid = _rand((n,), 3), _rand((m, n), 4)
     ref = torch.from_numpy(a).double() @ torch.from_numpy(w).double().t() + torch.from_numpy(bias).double()
@@ -48,6 +57,31 @@ def test_linear_bias_relu_residual(raw, precision, m, n, k):
     assert np.abs(planes - got).max() <= 2.0 ** -15 * np.abs(got).max()
 
 
+@pytest.mark.parametrize("m,n,k", [(10240, 512, 512), (9999, 1536, 512), (20000, 512, 2048)])
+def test_linear_pair_kernel_full_waves_and_split_tail(raw, monkeypatch, m, n, k):
+    """Sizes at which the library itself picks the CTA-pair kernel: several waves of 256 x 256 tiles and a
+    last partial wave cut into 128-column half tiles (80, 240 and 158 pair tiles on 74 pairs)."""
+    monkeypatch.delenv("FUNASR_B200_GEMM", raising=False)
+    a, w = _rand((m, k), 31), _rand((n, k), 32, k ** -0.5)
+    bias, resid = _rand((n,), 33), _rand((m, n), 34)
+    ref = torch.relu(torch.from_numpy(a).double() @ torch.from_numpy(w).double().t() + torch.from_numpy(bias).double())
+    ref = ref + torch.from_numpy(resid).double()
+    got, planes = raw.linear(a, w, bias, resid=resid, relu=True, precision="bf16x3", planes=True)
+    assert rel_err(got, ref) <= TOL["bf16x3"]
+    assert np.abs(planes - got).max() <= 2.0 ** -15 * np.abs(got).max()
+
+
+def test_vocab_argmax_pair_kernel_split_tail(raw, monkeypatch):
+    monkeypatch.delenv("FUNASR_B200_GEMM", raising=False)
+    m, n = 2000, 5037                      # 8 x 20 pair tiles: two full waves of 74 and 12 tiles cut in halves
+    a, w, bias = _rand((m, 512), 35), _rand((n, 512), 36, 512 ** -0.5), _rand((n,), 37, 0.1)
+    logits = torch.from_numpy(a).double() @ torch.from_numpy(w).double().t() + torch.from_numpy(bias).double()
+    top2 = logits.topk(2, -1).values
+    clear = ((top2[:, 0] - top2[:, 1]) > 1e-4).numpy()
+    ids = raw.vocab_argmax(a, w, bias, precision="bf16x3")
+    assert np.array_equal(ids[clear], logits.argmax(-1).numpy()[clear])
+
+
 def test_bf16x3_is_much_closer_than_bf16(raw):
     a, w, bias = _rand((256, 512), 5), _rand((512, 512), 6, 512 ** -0.5), _rand((512,), 7)
     ref = torch.from_numpy(a).double() @ torch.from_numpy(w).double().t() + torch.from_numpy(bias).double()
@@ -57,7 +91,9 @@ def test_bf16x3_is_much_closer_than_bf16(raw):
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
 @pytest.mark.parametrize("m,n", [(200, 5037), (131, 60515)])
-def test_vocab_argmax_never_materialises_logits(raw, precision, m, n):
+def test_vocab_argmax_never_materialises_logits(raw, gemm_kernel, precision, m, n):
+    if precision == "fp32" and gemm_kernel == "2cta":
+        pytest.skip("fp32 mode does not use the tensor-core kernels")
     a, w, bias = _rand((m, 512), 8), _rand((n, 512), 9, 512 ** -0.5), _rand((n,), 10, 0.1)
     logits = torch.from_numpy(a).double() @ torch.from_numpy(w).double().t() + torch.from_numpy(bias).double()
     top2 = logits.topk(2, -1).values
