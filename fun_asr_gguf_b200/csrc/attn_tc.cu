@@ -11,18 +11,28 @@
 // softmax weights p are all carried as bf16 hi/lo planes and every product is hi*hi + hi*lo + lo*hi
 // into an fp32 TMEM accumulator, like the projections.  The softmax itself is fp32.
 //
-// Two passes over the keys instead of an online rescale: pass 1 only takes the row maxima of S,
-// pass 2 recomputes S, forms p = exp2(S - max) and accumulates O = sum p v in TMEM with no
-// correction step.  That costs one extra QK^T (tensor time 9 instead of 6 units) but removes the
-// TMEM read-modify-write of O and every dependency between a tile's softmax and the previous PV.
+// Two passes over the keys instead of an online rescale.  Pass 1 only needs a shift that keeps exp2 in
+// range, not the exact row maximum (softmax is invariant to the shift), so it runs ONE product,
+// q_hi k_hi^T, and loads only the hi plane of K.  Pass 2 computes S with all three products, forms
+// p = exp2(S - shift) and accumulates O = sum p v in TMEM with no correction step.  Tensor work per key
+// tile: 1 + 3 + 3 units instead of the 6 + rescale of an online softmax in this precision.
+//
+// Both left operands live in TENSOR MEMORY, not shared memory (tcgen05.mma with A from TMEM): the
+// query tile is written there once per item and the softmax weights once per key tile, straight
+// from the registers that produced them.  The tensor core then reads only K or V from shared memory
+// (2-4 KB per instruction instead of 6-8 KB), which is what bounded the first version of this kernel,
+// and P never takes the detour through a swizzled smem tile and a proxy fence.
 //
 // One CTA per SM, persistent over (segment, head, 128-query tile) items:
-//   warp 0      TMA: Q planes once per item; 64-key K / V tiles into a 4-slot ring (pass 1: four K tiles in
-//               flight; pass 2: K in slots 0-1, freed as soon as S is issued, V in slots 2-3, freed after PV)
-//   warp 1      TMEM allocator + MMA issuer: S = Q K^T (M128 x N64, K-major both) into a double-buffered
-//               TMEM tile, O += P V (M128 x N d_k, P from smem K-major, V from smem MN-major: no transpose)
+//   warp 0      TMA: 64-key K / V tiles (both planes; pass 1: hi plane only) into a 6-slot ring, in the
+//               order the MMA warp consumes them
+//   warp 1      TMEM allocator + MMA issuer: S = Q K^T (M128 x N64) into a double-buffered TMEM tile,
+//               O += P V (M128 x N d_k, V from smem MN-major: no transpose)
 //   warps 2..5  softmax: thread = query row = TMEM lane; tcgen05.ld S, max / exp2 / sum, split p into
-//               hi/lo planes written to smem in the UMMA SWIZZLE_128B layout; final 1/l scaling and store
+//               hi/lo planes, tcgen05.st into a double-buffered P tile
+//   warps 6..9  query loader (global -> registers -> TMEM, next item's Q while the current item finishes
+//               its PV products) and output epilogue (O / l -> bf16 planes or fp32)
+// TMEM columns: S0 0, S1 64, O 128, P0 256 (hi 32 | lo 32), P1 320, Q 384 (hi d_k/2 | lo d_k/2).
 #include "kernels.h"
 #include "tc_ptx.cuh"
 
@@ -32,21 +42,21 @@ namespace {
 
 constexpr int QT = 128;          // queries per item (UMMA M)
 constexpr int KT = 64;           // keys per tile (UMMA N for S, K extent for PV)
-constexpr int kAttThreads = 192;
+constexpr int kAttThreads = 320;
+constexpr int kSlots = 6;
 
 template <int DK> struct ACfg {
-    static constexpr int kChunks = DK / 64;                 // 128-byte column chunks per head row
-    static constexpr int kQBytes = 2 * kChunks * QT * 128;   // planes x chunks x rows x 128 B
-    static constexpr int kKBytes = 2 * kChunks * KT * 128;   // one 64-key tile of K (or V), both planes
-    static constexpr int kSlots = 4;                         // pass 1: four K tiles in flight; pass 2: K in slots 0-1, V in 2-3
-    static constexpr int kPBytes = 2 * QT * 128;             // planes x rows x (64 keys * 2 B)
-    static constexpr int kSmemBytes = kQBytes + kSlots * kKBytes + kPBytes + 1024 + 256;
-    static constexpr uint32_t kTmemCols = 256;                      // S0 [0,64) | S1 [64,128) | O [128,128+DK)
-    static constexpr uint32_t kOCol = 128;
+    static constexpr int kChunks = DK / 64;                  // 128-byte column chunks per head row
+    static constexpr int kPlaneBytes = kChunks * KT * 128;   // one plane of a 64-key tile of K (or V)
+    static constexpr int kSlotBytes = 2 * kPlaneBytes;       // both planes
+    static constexpr int kSmemBytes = kSlots * kSlotBytes + 2 * QT * 4 /*row sums*/ + 1024 + 256;
+    static constexpr uint32_t kTmemCols = 512;
+    static constexpr uint32_t kSCol = 0, kOCol = 128, kPCol = 256, kQCol = 384;
+    static constexpr uint32_t kQPlaneCols = DK / 2;          // packed bf16 pairs
 };
 
-// 2^x for x <= 0 on the MUFU pipe (2 ulp); denormal results flush to zero, which is what a vanishing
-// softmax weight should do.
+// 2^x on the MUFU pipe (2 ulp); denormal results flush to zero, which is what a vanishing softmax
+// weight should do.
 __device__ __forceinline__ float fast_exp2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -55,6 +65,8 @@ __device__ __forceinline__ float fast_exp2(float x) {
 
 struct AttnParams {
     int batch, frames, heads, d_model, ld;     // ld = row stride (elements) of the qkv planes
+    const __nv_bfloat16* q_hi;                 // plane pointers of the fused q|k|v matrix (q at column 0)
+    const __nv_bfloat16* q_lo;
     const int* kv_len;
     float* ctx;
     __nv_bfloat16* ctx_hi;
@@ -64,36 +76,38 @@ struct AttnParams {
 
 template <int DK>
 __global__ void __launch_bounds__(kAttThreads, 1)
-k_attention_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
+k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
     using C = ACfg<DK>;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
-    const uint32_t q_base = (raw + 1023u) & ~1023u;
-    const uint32_t kv_base = q_base + C::kQBytes;
-    const uint32_t p_base = kv_base + C::kSlots * C::kKBytes;
-    const uint32_t bars = p_base + C::kPBytes;
-    const uint32_t bar_qfull = bars, bar_qempty = bars + 8;
-    const uint32_t bar_kvfull = bars + 16, bar_kvempty = bars + 48;       // [4] each: one pair per ring slot
-    const uint32_t bar_sfull = bars + 80, bar_sempty = bars + 96;         // [2] each
-    const uint32_t bar_pfull = bars + 112, bar_pempty = bars + 120;
-    const uint32_t bar_ofull = bars + 128, bar_oempty = bars + 136;
-    const uint32_t tmem_slot = bars + 144;
+    const uint32_t kv_base = (raw + 1023u) & ~1023u;
+    const uint32_t l_base = kv_base + kSlots * C::kSlotBytes;              // float[2][128] row sums, by item parity
+    const uint32_t bars = l_base + 2 * QT * 4;
+    const uint32_t bar_kvfull = bars, bar_kvempty = bars + 8 * kSlots;   // [kSlots] each
+    const uint32_t bar_sfull = bars + 16 * kSlots, bar_sempty = bar_sfull + 16;   // [2] each
+    const uint32_t bar_pfull = bar_sempty + 16, bar_pempty = bar_pfull + 16;      // [2] each
+    const uint32_t bar_qfull = bar_pempty + 16, bar_qempty = bar_qfull + 8;
+    const uint32_t bar_ofull = bar_qempty + 8, bar_oempty = bar_ofull + 8;
+    const uint32_t bar_lfull = bar_oempty + 8;                           // [2]
+    const uint32_t tmem_slot = bar_lfull + 16;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
-    unsigned char* p_ptr = smem_raw + (p_base - raw);
+    float* l_smem = reinterpret_cast<float*>(smem_raw + (l_base - raw));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q_tiles = (p.frames + QT - 1) / QT;
     const int items = p.batch * p.heads * q_tiles;
 
     if (threadIdx.x == 0) {
-        mbar_init(bar_qfull, 1); mbar_init(bar_qempty, 1);
-        for (int s = 0; s < 4; ++s) { mbar_init(bar_kvfull + 8 * s, 1); mbar_init(bar_kvempty + 8 * s, 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(bar_sfull + 8 * s, 1); mbar_init(bar_sempty + 8 * s, 4); }
-        mbar_init(bar_pfull, 4); mbar_init(bar_pempty, 1);
+        for (int s = 0; s < kSlots; ++s) { mbar_init(bar_kvfull + 8 * s, 1); mbar_init(bar_kvempty + 8 * s, 1); }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(bar_sfull + 8 * s, 1); mbar_init(bar_sempty + 8 * s, 4);
+            mbar_init(bar_pfull + 8 * s, 4); mbar_init(bar_pempty + 8 * s, 1);
+            mbar_init(bar_lfull + 8 * s, 4);
+        }
+        mbar_init(bar_qfull, 4); mbar_init(bar_qempty, 1);
         mbar_init(bar_ofull, 1); mbar_init(bar_oempty, 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_async_smem();
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_kv) : "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, C::kTmemCols);
@@ -115,35 +129,28 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     if (warp == 0) {
         // ================================================================== TMA producer
         if (lane == 0) {
-            uint32_t item_it = 0, fills = 0;          // bit s of `fills`: parity of how often slot s has been filled
-            // one 64-key tile of K (which = 1) or V (which = 2), both planes, into ring slot `slot`
-            auto load_tile = [&](int slot, int which, int h, int row) {
-                mbar_wait(bar_kvempty + 8 * slot, ((fills >> slot) & 1) ^ 1);
-                const uint32_t full = bar_kvfull + 8 * slot, sb = kv_base + slot * C::kKBytes;
-                mbar_arrive_expect_tx(full, C::kKBytes);
-#pragma unroll
-                for (int pl = 0; pl < 2; ++pl)
+            uint32_t cnt = 0;                         // tiles produced so far: slot = cnt % kSlots
+            // one 64-key tile of K (which = 1) or V (which = 2), `planes` planes, into the next ring slot
+            auto load_tile = [&](int which, int planes, int h, int row) {
+                const uint32_t slot = cnt % kSlots, ph = (cnt / kSlots) & 1;
+                mbar_wait(bar_kvempty + 8 * slot, ph ^ 1);
+                const uint32_t full = bar_kvfull + 8 * slot, sb = kv_base + slot * C::kSlotBytes;
+                mbar_arrive_expect_tx(full, planes * C::kPlaneBytes);
+                for (int pl = 0; pl < planes; ++pl)
 #pragma unroll
                     for (int c = 0; c < C::kChunks; ++c)
                         tma_load_3d(sb + (pl * C::kChunks + c) * KT * 128, &map_kv, full, which * p.d_model + h * DK + c * 64, row, pl);
-                fills ^= 1u << slot;
+                ++cnt;
             };
-            for (int item = blockIdx.x; item < items; item += gridDim.x, ++item_it) {
+            for (int item = blockIdx.x; item < items; item += gridDim.x) {
                 int b, h, qt, n, klen;
                 decode(item, b, h, qt, n, klen);
                 const int row0 = b * p.frames;
-                mbar_wait(bar_qempty, (item_it & 1) ^ 1);
-                mbar_arrive_expect_tx(bar_qfull, C::kQBytes);
-#pragma unroll
-                for (int pl = 0; pl < 2; ++pl)
-#pragma unroll
-                    for (int c = 0; c < C::kChunks; ++c)
-                        tma_load_3d(q_base + (pl * C::kChunks + c) * QT * 128, &map_q, bar_qfull, h * DK + c * 64,
-                                    row0 + qt * QT, pl);
-                for (int j = 0; j < n; ++j) load_tile(j & 3, 1, h, row0 + j * KT);             // pass 1: K only
-                for (int j = 0; j < n; ++j) {                                                  // pass 2: K then V
-                    load_tile(j & 1, 1, h, row0 + j * KT);
-                    load_tile(2 + (j & 1), 2, h, row0 + j * KT);
+                for (int j = 0; j < n; ++j) load_tile(1, 1, h, row0 + j * KT);                 // pass 1: K hi plane
+                load_tile(1, 2, h, row0);                                                      // pass 2: K0, then K(j+1), V(j)
+                for (int j = 0; j < n; ++j) {
+                    if (j + 1 < n) load_tile(1, 2, h, row0 + (j + 1) * KT);
+                    load_tile(2, 2, h, row0 + j * KT);
                 }
             }
         }
@@ -153,86 +160,82 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         if (lane == 0) {
             constexpr uint32_t kIdescS = umma_idesc_bf16(QT, KT, false);
             constexpr uint32_t kIdescO = umma_idesc_bf16(QT, DK, true);
-            uint32_t item_it = 0, uses = 0, s_it = 0, p_it = 0;   // bit s of `uses`: parity of how often slot s has been consumed
-            // S[sbuf] = Q K^T over the K planes in `slot`: lo*hi, hi*lo, then hi*hi
-            auto issue_s = [&](int slot, uint32_t sbuf) {
-                const uint32_t stage_base = kv_base + slot * C::kKBytes;
-                const uint32_t tmem_s = tmem_base + sbuf * KT;
+            const uint32_t tmem_q = tmem_base + C::kQCol, tmem_o = tmem_base + C::kOCol;
+            uint32_t item_it = 0, cnt = 0, s_it = 0, p_it = 0;
+            // S[sbuf] = Q K^T over the K planes in the next ring slot; terms = 1: hi*hi only (pass 1), 3: lo*hi, hi*lo, hi*hi
+            auto do_s = [&](int terms) {
+                const uint32_t slot = cnt % kSlots, ph = (cnt / kSlots) & 1;
+                const uint32_t sbuf = s_it & 1;
+                mbar_wait(bar_kvfull + 8 * slot, ph);
+                mbar_wait(bar_sempty + 8 * sbuf, ((s_it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t stage_base = kv_base + slot * C::kSlotBytes;
+                const uint32_t tmem_s = tmem_base + C::kSCol + sbuf * KT;
                 uint32_t accum = 0;
-#pragma unroll
-                for (int term = 0; term < 3; ++term) {
+                for (int term = 3 - terms; term < 3; ++term) {
                     const int qa = term == 0 ? 1 : 0, kb = term == 1 ? 1 : 0;     // plane of Q, plane of K
 #pragma unroll
                     for (int ks = 0; ks < DK / 16; ++ks) {
                         const int c = ks >> 2, o = (ks & 3) * 32;
-                        const uint64_t da = umma_desc(q_base + (qa * C::kChunks + c) * QT * 128 + o, 16, 1024);
                         const uint64_t db = umma_desc(stage_base + (kb * C::kChunks + c) * KT * 128 + o, 16, 1024);
-                        tc_mma(tmem_s, da, db, kIdescS, accum);
+                        tc_mma_ts(tmem_s, tmem_q + qa * C::kQPlaneCols + ks * 8, db, kIdescS, accum);
                         accum = 1;
                     }
                 }
-            };
-            // wait for K in `slot` and a free S buffer, issue S, signal the softmax warps, free the slot
-            auto do_s = [&](int slot) {
-                const uint32_t sbuf = s_it & 1;
-                mbar_wait(bar_kvfull + 8 * slot, (uses >> slot) & 1);
-                mbar_wait(bar_sempty + 8 * sbuf, ((s_it >> 1) & 1) ^ 1);
-                tc_fence_after();
-                issue_s(slot, sbuf);
                 tc_commit(bar_sfull + 8 * sbuf);
                 tc_commit(bar_kvempty + 8 * slot);
-                uses ^= 1u << slot;
+                ++cnt;
                 ++s_it;
             };
             for (int item = blockIdx.x; item < items; item += gridDim.x, ++item_it) {
                 int b, h, qt, n, klen;
                 decode(item, b, h, qt, n, klen);
-                mbar_wait(bar_qfull, item_it & 1);
+                mbar_wait(bar_qfull, item_it & 1);                  // this item's Q is in TMEM
                 tc_fence_after();
-                for (int j = 0; j < n; ++j) do_s(j & 3);            // ---- pass 1: row maxima
+                for (int j = 0; j < n; ++j) do_s(1);                // ---- pass 1: shift = max of the hi*hi scores
                 // ---- pass 2: S runs one tile ahead of PV
-                do_s(0);
+                do_s(3);
                 if (n == 1) tc_commit(bar_qempty);                  // last read of Q: the next item's Q may land
                 mbar_wait(bar_oempty, (item_it & 1) ^ 1);           // previous item's O has been read out
                 tc_fence_after();
                 for (int j = 0; j < n; ++j, ++p_it) {
                     if (j + 1 < n) {
-                        do_s((j + 1) & 1);
+                        do_s(3);
                         if (j + 2 == n) tc_commit(bar_qempty);
                     }
-                    const int vslot = 2 + (j & 1);
-                    const uint32_t v_base = kv_base + vslot * C::kKBytes;
-                    mbar_wait(bar_kvfull + 8 * vslot, (uses >> vslot) & 1);
-                    mbar_wait(bar_pfull, p_it & 1);
+                    const uint32_t slot = cnt % kSlots, ph = (cnt / kSlots) & 1;
+                    const uint32_t pbuf = p_it & 1;
+                    const uint32_t v_base = kv_base + slot * C::kSlotBytes;
+                    mbar_wait(bar_kvfull + 8 * slot, ph);
+                    mbar_wait(bar_pfull + 8 * pbuf, (p_it >> 1) & 1);
                     tc_fence_after();
-                    const uint32_t tmem_o = tmem_base + C::kOCol;
+                    const uint32_t tmem_p = tmem_base + C::kPCol + pbuf * 64;
                     uint32_t accum = j > 0 ? 1u : 0u;
 #pragma unroll
                     for (int term = 0; term < 3; ++term) {
                         const int pa = term == 0 ? 1 : 0, vb = term == 1 ? 1 : 0;  // plane of P, plane of V
 #pragma unroll
                         for (int ks = 0; ks < KT / 16; ++ks) {
-                            // A = P [128 q][64 keys] K-major; B = V [16 keys][DK] MN-major: 64-column chunks
+                            // A = P [128 q][16 keys] from TMEM; B = V [16 keys][DK] MN-major: 64-column chunks
                             // KT*128 B apart (LBO), 8-key groups 1024 B apart (SBO)
-                            const uint64_t da = umma_desc(p_base + pa * QT * 128 + ks * 32, 16, 1024);
-                            const uint64_t db = umma_desc(v_base + vb * C::kChunks * KT * 128 + ks * 16 * 128, KT * 128, 1024);
-                            tc_mma(tmem_o, da, db, kIdescO, accum);
+                            const uint64_t db = umma_desc(v_base + vb * C::kPlaneBytes + ks * 16 * 128, KT * 128, 1024);
+                            tc_mma_ts(tmem_o, tmem_p + pa * 32 + ks * 8, db, kIdescO, accum);
                             accum = 1;
                         }
                     }
-                    tc_commit(bar_pempty);
-                    tc_commit(bar_kvempty + 8 * vslot);
-                    uses ^= 1u << vslot;
+                    tc_commit(bar_pempty + 8 * pbuf);
+                    tc_commit(bar_kvempty + 8 * slot);
+                    ++cnt;
                 }
                 tc_commit(bar_ofull);
             }
         }
         __syncwarp();
-    } else {
-        // ================================================================== softmax + epilogue
-        const int lane_grp = warp & 3;
-        const int r = lane_grp * 32 + lane;                         // query row in the tile == TMEM lane
-        const uint32_t lane_addr = (uint32_t)(lane_grp * 32) << 16;
+    } else if (warp < 6) {
+        // ================================================================== softmax
+        const int quarter = warp & 3;
+        const int r = quarter * 32 + lane;                          // query row in the tile == TMEM lane
+        const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
         uint32_t item_it = 0, s_it = 0, p_it = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x, ++item_it) {
             int b, h, qt, n, klen;
@@ -244,8 +247,8 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                 mbar_wait(bar_sfull + 8 * sbuf, (s_it >> 1) & 1);
                 tc_fence_after();
                 uint32_t s0[32], s1[32];
-                tc_ld32(tmem_base + lane_addr + sbuf * KT, s0);
-                tc_ld32(tmem_base + lane_addr + sbuf * KT + 32, s1);
+                tc_ld32(tmem_base + lane_addr + C::kSCol + sbuf * KT, s0);
+                tc_ld32(tmem_base + lane_addr + C::kSCol + sbuf * KT + 32, s1);
                 tc_wait_ld();
                 tc_fence_before();
                 __syncwarp();
@@ -265,19 +268,19 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             // ---- pass 2
             float lsum = 0.f;
             for (int j = 0; j < n; ++j, ++s_it, ++p_it) {
-                const uint32_t sbuf = s_it & 1;
+                const uint32_t sbuf = s_it & 1, pbuf = p_it & 1;
                 mbar_wait(bar_sfull + 8 * sbuf, (s_it >> 1) & 1);
                 tc_fence_after();
                 uint32_t s0[32], s1[32];
-                tc_ld32(tmem_base + lane_addr + sbuf * KT, s0);
-                tc_ld32(tmem_base + lane_addr + sbuf * KT + 32, s1);
+                tc_ld32(tmem_base + lane_addr + C::kSCol + sbuf * KT, s0);
+                tc_ld32(tmem_base + lane_addr + C::kSCol + sbuf * KT + 32, s1);
                 tc_wait_ld();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_sempty + 8 * sbuf);
                 const int kbase = j * KT;
                 const bool full_tile = kbase + KT <= klen;
-                uint32_t hi[32], lo[32];                             // 64 keys x bf16, packed in pairs
+                uint32_t hi[32], lo[32];                             // 64 keys x bf16, packed in pairs (even key in the low half)
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                     const int half = i >> 4, w = (i & 15) * 2;       // word i covers keys 2i, 2i+1
@@ -291,24 +294,68 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                     lsum += p0 + p1;
                     split_bf16x2(p0, p1, hi[i], lo[i]);
                 }
-                mbar_wait(bar_pempty, (p_it & 1) ^ 1);               // PV of the previous tile has consumed P
-                // row r of the K-major SWIZZLE_128B tile: 16-byte chunk c lives at chunk c ^ (r & 7)
-                unsigned char* prow_hi = p_ptr + r * 128;
-                unsigned char* prow_lo = p_ptr + QT * 128 + r * 128;
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const int pc = (c ^ (r & 7)) * 16;
-                    *reinterpret_cast<uint4*>(prow_hi + pc) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
-                    *reinterpret_cast<uint4*>(prow_lo + pc) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
-                }
-                fence_async_smem();                                  // generic-proxy writes -> visible to the tensor core
+                mbar_wait(bar_pempty + 8 * pbuf, ((p_it >> 1) & 1) ^ 1);   // the PV that read this P buffer has retired
+                tc_fence_after();
+                const uint32_t tp = tmem_base + lane_addr + C::kPCol + pbuf * 64;
+                tc_st32(tp, hi);
+                tc_st32(tp + 32, lo);
+                tc_wait_st();
+                tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_pfull);
+                if (lane == 0) mbar_arrive(bar_pfull + 8 * pbuf);
+            }
+            // ---- hand the row sums to the epilogue warps
+            l_smem[(item_it & 1) * QT + r] = lsum;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_lfull + 8 * (item_it & 1));
+        }
+    } else {
+        // ================================================================== query loader + output epilogue
+        const int quarter = warp & 3;
+        const int r = quarter * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+        // Q rows of one item, both planes, global -> registers -> TMEM columns kQCol..: word c of a plane = elements 2c, 2c+1
+        auto load_q = [&](int item) {
+            int b, h, qt, n, klen;
+            decode(item, b, h, qt, n, klen);
+            const int row = qt * QT + r;
+            const bool ok = row < p.frames;
+            const int64_t off = ((int64_t)b * p.frames + row) * p.ld + h * DK;
+#pragma unroll
+            for (int pl = 0; pl < 2; ++pl) {
+                const uint4* src = reinterpret_cast<const uint4*>((pl ? p.q_lo : p.q_hi) + off);
+#pragma unroll
+                for (int g = 0; g < DK / 64; ++g) {                 // 32 words = 64 elements per store
+                    uint32_t w[32];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const uint4 v = ok ? __ldg(src + g * 8 + i) : make_uint4(0u, 0u, 0u, 0u);
+                        w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+                    }
+                    tc_st32(tmem_base + lane_addr + C::kQCol + pl * C::kQPlaneCols + g * 32, w);
+                }
+            }
+            tc_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_qfull);
+        };
+        uint32_t item_it = 0;
+        if ((int)blockIdx.x < items) load_q(blockIdx.x);
+        for (int item = blockIdx.x; item < items; item += gridDim.x, ++item_it) {
+            int b, h, qt, n, klen;
+            decode(item, b, h, qt, n, klen);
+            const int next = item + gridDim.x;
+            if (next < items) {
+                mbar_wait(bar_qempty, item_it & 1);                 // every S product of this item has retired
+                tc_fence_after();
+                load_q(next);
             }
             // ---- epilogue: O / l
             mbar_wait(bar_ofull, item_it & 1);
+            mbar_wait(bar_lfull + 8 * (item_it & 1), (item_it >> 1) & 1);
             tc_fence_after();
-            const float inv = 1.0f / lsum;
+            const float inv = 1.0f / l_smem[(item_it & 1) * QT + r];
             const int row = qt * QT + r;
             const int64_t grow = (int64_t)b * p.frames + row;
 #pragma unroll 1
@@ -370,20 +417,20 @@ void launch_attention_tc(Planes qkv, int64_t plane_stride, int ld, int d_model, 
     FA_REQUIRE(dk == 64 || dk == 128, "attention head width must be 64 or 128");
     FA_REQUIRE(heads * dk == d_model, "heads * d_k must equal the model width");
     FA_REQUIRE(ldo % 8 == 0 && ld % 8 == 0, "attention strides must be multiples of 8");
+    FA_REQUIRE(qkv.lo == qkv.hi + plane_stride, "attention expects the lo plane `plane_stride` elements after the hi plane");
     const int rows = batch * frames;
-    // one tensor per use: the q map fetches 128-row boxes, the k/v map 64-row boxes
-    const TcOperand mq = tc_make_operand(qkv.hi, rows, ld, ld, plane_stride, 2, QT);
-    const TcOperand mkv = tc_make_operand(qkv.hi, rows, ld, ld, plane_stride, 2, KT);
+    const TcOperand mkv = tc_make_operand(qkv.hi, rows, ld, ld, plane_stride, 2, KT);     // 64-row boxes of k and v
     AttnParams p{};
     p.batch = batch; p.frames = frames; p.heads = heads; p.d_model = d_model; p.ld = ld; p.kv_len = kv_len;
+    p.q_hi = qkv.hi; p.q_lo = qkv.lo;
     p.ctx = ctx_f32; p.ctx_hi = ctx_pl.hi; p.ctx_lo = ctx_pl.lo; p.ldo = ldo;
     const int items = batch * heads * cdiv(frames, QT);
     const int grid = items < g_att_sms ? items : g_att_sms;
     prof_note_work(4.0 * batch * heads * (double)frames * frames * dk, 0.0);
     if (dk == 128) {
-        FA_LAUNCH(k_attention_tc<128>, grid, kAttThreads, ACfg<128>::kSmemBytes, st, mq.map, mkv.map, p);
+        FA_LAUNCH(k_attention_tc<128>, grid, kAttThreads, ACfg<128>::kSmemBytes, st, mkv.map, p);
     } else {
-        FA_LAUNCH(k_attention_tc<64>, grid, kAttThreads, ACfg<64>::kSmemBytes, st, mq.map, mkv.map, p);
+        FA_LAUNCH(k_attention_tc<64>, grid, kAttThreads, ACfg<64>::kSmemBytes, st, mkv.map, p);
     }
 }
 
