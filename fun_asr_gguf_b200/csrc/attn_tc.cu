@@ -17,22 +17,29 @@
 // p = exp2(S - shift) and accumulates O = sum p v in TMEM with no correction step.  Tensor work per key
 // tile: 1 + 3 + 3 units instead of the 6 + rescale of an online softmax in this precision.
 //
-// Both left operands live in TENSOR MEMORY, not shared memory (tcgen05.mma with A from TMEM): the
-// query tile is written there once per item and the softmax weights once per key tile, straight
-// from the registers that produced them.  The tensor core then reads only K or V from shared memory
-// (2-4 KB per instruction instead of 6-8 KB), which is what bounded the first version of this kernel,
-// and P never takes the detour through a swizzled smem tile and a proxy fence.
+// Shapes follow what the tensor core was measured to sustain on B200 (tools/umma_bench.cu, cycles per
+// M128 x N x K16 bf16 instruction): A from shared memory 83 / 97 / 161 for N = 64 / 128 / 256, A from
+// tensor memory 65 / 72 / 136.  So both left operands live in TENSOR MEMORY (tcgen05.mma with A from
+// TMEM) — the query tile is written there once per item, the softmax weights once per key tile,
+// straight from the registers that produced them, IN PLACE over the scores they came from — and a key
+// tile is 128 keys, so every instruction is N = 128.
 //
 // One CTA per SM, persistent over (segment, head, 128-query tile) items:
-//   warp 0      TMA: 64-key K / V tiles (both planes; pass 1: hi plane only) into a 6-slot ring, in the
-//               order the MMA warp consumes them
-//   warp 1      TMEM allocator + MMA issuer: S = Q K^T (M128 x N64) into a double-buffered TMEM tile,
-//               O += P V (M128 x N d_k, V from smem MN-major: no transpose)
-//   warps 2..5  softmax: thread = query row = TMEM lane; tcgen05.ld S, max / exp2 / sum, split p into
-//               hi/lo planes, tcgen05.st into a double-buffered P tile
-//   warps 6..9  query loader (global -> registers -> TMEM, next item's Q while the current item finishes
-//               its PV products) and output epilogue (O / l -> bf16 planes or fp32)
-// TMEM columns: S0 0, S1 64, O 128, P0 256 (hi 32 | lo 32), P1 320, Q 384 (hi d_k/2 | lo d_k/2).
+//   warp 0       TMA: one plane of a 128-key K or V tile per ring slot (6 slots), in the order the MMA warp
+//                consumes them; pass 1 loads the hi plane of K only
+//   warp 1       TMEM allocator + MMA issuer (all lanes walk the loop, one elected lane issues):
+//                S = Q K^T (M128 x N128) into two score tiles, O += P V (M128 x N d_k, V from smem MN-major:
+//                no transpose).  The tensor pipe executes in issue order, which is what lets S(j+2) reuse
+//                the tile P(j) lives in without a barrier: it is issued after P(j) V(j).
+//   warps 2..5   softmax group 0: even key tiles, score tile 0
+//   warps 6..9   softmax group 1: odd key tiles, score tile 1
+//                (thread = query row = TMEM lane; tcgen05.ld 32 scores, exp2 / sum, split p into hi/lo planes,
+//                tcgen05.st over the same 32 columns.  The groups exchange row maxima after pass 1 and add
+//                their row sums at the end.)
+//   warps 10..13 query loader (global -> registers -> TMEM, next item's Q while the current item finishes
+//                its PV products) and output epilogue (O / l -> bf16 planes or fp32)
+// TMEM columns: score/weight tile 0 at 0, tile 1 at 128, O at 256, Q at 384 (hi d_k/2 | lo d_k/2).
+// Inside a score tile, keys 32c .. 32c+31 become: hi pairs in columns 32c .. +15, lo pairs in 32c+16 .. +31.
 #include "kernels.h"
 #include "tc_ptx.cuh"
 
@@ -41,17 +48,16 @@ namespace fa {
 namespace {
 
 constexpr int QT = 128;          // queries per item (UMMA M)
-constexpr int KT = 64;           // keys per tile (UMMA N for S, K extent for PV)
-constexpr int kAttThreads = 320;
+constexpr int KT = 128;          // keys per tile (UMMA N for S, K extent for PV)
+constexpr int kAttThreads = 448;
 constexpr int kSlots = 6;
 
 template <int DK> struct ACfg {
     static constexpr int kChunks = DK / 64;                  // 128-byte column chunks per head row
-    static constexpr int kPlaneBytes = kChunks * KT * 128;   // one plane of a 64-key tile of K (or V)
-    static constexpr int kSlotBytes = 2 * kPlaneBytes;       // both planes
-    static constexpr int kSmemBytes = kSlots * kSlotBytes + 2 * QT * 4 /*row sums*/ + 1024 + 256;
+    static constexpr int kSlotBytes = kChunks * KT * 128;    // one plane of a 128-key tile of K (or V)
+    static constexpr int kSmemBytes = kSlots * kSlotBytes + 8 * QT * 4 /*row sums and maxima*/ + 1024 + 256;
     static constexpr uint32_t kTmemCols = 512;
-    static constexpr uint32_t kSCol = 0, kOCol = 128, kPCol = 256, kQCol = 384;
+    static constexpr uint32_t kSCol = 0, kOCol = 256, kQCol = 384;
     static constexpr uint32_t kQPlaneCols = DK / 2;          // packed bf16 pairs
 };
 
@@ -81,19 +87,20 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t kv_base = (raw + 1023u) & ~1023u;
-    const uint32_t l_base = kv_base + kSlots * C::kSlotBytes;              // float[2][128] row sums, by item parity
-    const uint32_t bars = l_base + 2 * QT * 4;
+    const uint32_t l_base = kv_base + kSlots * C::kSlotBytes;              // float[2 item parities][2 groups][128]: row sums, then row maxima
+    const uint32_t bars = l_base + 8 * QT * 4;
     const uint32_t bar_kvfull = bars, bar_kvempty = bars + 8 * kSlots;   // [kSlots] each
     const uint32_t bar_sfull = bars + 16 * kSlots, bar_sempty = bar_sfull + 16;   // [2] each
-    const uint32_t bar_pfull = bar_sempty + 16, bar_pempty = bar_pfull + 16;      // [2] each
-    const uint32_t bar_qfull = bar_pempty + 16, bar_qempty = bar_qfull + 8;
+    const uint32_t bar_pfull = bar_sempty + 16;                          // [2]
+    const uint32_t bar_qfull = bar_pfull + 16, bar_qempty = bar_qfull + 8;
     const uint32_t bar_ofull = bar_qempty + 8, bar_oempty = bar_ofull + 8;
     const uint32_t bar_lfull = bar_oempty + 8;                           // [2]
     const uint32_t tmem_slot = bar_lfull + 16;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
     float* l_smem = reinterpret_cast<float*>(smem_raw + (l_base - raw));
+    float* mx_smem = l_smem + 4 * QT;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     const int q_tiles = (p.frames + QT - 1) / QT;
     const int items = p.batch * p.heads * q_tiles;
 
@@ -101,8 +108,8 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
         for (int s = 0; s < kSlots; ++s) { mbar_init(bar_kvfull + 8 * s, 1); mbar_init(bar_kvempty + 8 * s, 1); }
         for (int s = 0; s < 2; ++s) {
             mbar_init(bar_sfull + 8 * s, 1); mbar_init(bar_sempty + 8 * s, 4);
-            mbar_init(bar_pfull + 8 * s, 4); mbar_init(bar_pempty + 8 * s, 1);
-            mbar_init(bar_lfull + 8 * s, 4);
+            mbar_init(bar_pfull + 8 * s, 4);
+            mbar_init(bar_lfull + 8 * s, 8);
         }
         mbar_init(bar_qfull, 4); mbar_init(bar_qempty, 1);
         mbar_init(bar_ofull, 1); mbar_init(bar_oempty, 4);
@@ -114,7 +121,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot_ptr;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_ptr, 0);    // provably warp-uniform
 
     // item -> (segment b, head h, query tile qt); key tiles n
     auto decode = [&](int item, int& b, int& h, int& qt, int& n, int& klen) {
@@ -128,184 +135,208 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
 
     if (warp == 0) {
         // ================================================================== TMA producer
-        if (lane == 0) {
-            uint32_t cnt = 0;                         // tiles produced so far: slot = cnt % kSlots
-            // one 64-key tile of K (which = 1) or V (which = 2), `planes` planes, into the next ring slot
-            auto load_tile = [&](int which, int planes, int h, int row) {
-                const uint32_t slot = cnt % kSlots, ph = (cnt / kSlots) & 1;
-                mbar_wait(bar_kvempty + 8 * slot, ph ^ 1);
-                const uint32_t full = bar_kvfull + 8 * slot, sb = kv_base + slot * C::kSlotBytes;
-                mbar_arrive_expect_tx(full, planes * C::kPlaneBytes);
-                for (int pl = 0; pl < planes; ++pl)
+        uint32_t cnt = 0;                             // slots produced so far: slot = cnt % kSlots
+        // plane `pl` of the 128-key tile of K (which = 1) or V (which = 2) starting at `row`, into the next ring slot
+        auto load_plane = [&](int which, int pl, int h, int row) {
+            const uint32_t slot = cnt % kSlots, ph = (cnt / kSlots) & 1;
+            mbar_wait(bar_kvempty + 8 * slot, ph ^ 1);
+            const uint32_t full = bar_kvfull + 8 * slot, sb = kv_base + slot * C::kSlotBytes;
+            if (elect_one()) {
+                mbar_arrive_expect_tx(full, C::kSlotBytes);
 #pragma unroll
-                    for (int c = 0; c < C::kChunks; ++c)
-                        tma_load_3d(sb + (pl * C::kChunks + c) * KT * 128, &map_kv, full, which * p.d_model + h * DK + c * 64, row, pl);
-                ++cnt;
-            };
-            for (int item = blockIdx.x; item < items; item += gridDim.x) {
-                int b, h, qt, n, klen;
-                decode(item, b, h, qt, n, klen);
-                const int row0 = b * p.frames;
-                for (int j = 0; j < n; ++j) load_tile(1, 1, h, row0 + j * KT);                 // pass 1: K hi plane
-                load_tile(1, 2, h, row0);                                                      // pass 2: K0, then K(j+1), V(j)
-                for (int j = 0; j < n; ++j) {
-                    if (j + 1 < n) load_tile(1, 2, h, row0 + (j + 1) * KT);
-                    load_tile(2, 2, h, row0 + j * KT);
+                for (int c = 0; c < C::kChunks; ++c)
+                    tma_load_3d(sb + c * KT * 128, &map_kv, full, which * p.d_model + h * DK + c * 64, row, pl);
+            }
+            __syncwarp();
+            ++cnt;
+        };
+        for (int item = blockIdx.x; item < items; item += gridDim.x) {
+            int b, h, qt, n, klen;
+            decode(item, b, h, qt, n, klen);
+            const int row0 = b * p.frames;
+            for (int j = 0; j < n; ++j) load_plane(1, 0, h, row0 + j * KT);                    // pass 1: K hi
+            for (int j = 0; j < 2 && j < n; ++j) {                                             // pass 2: K0, K1, then V(j), K(j+2)
+                load_plane(1, 0, h, row0 + j * KT);
+                load_plane(1, 1, h, row0 + j * KT);
+            }
+            for (int j = 0; j < n; ++j) {
+                load_plane(2, 0, h, row0 + j * KT);
+                load_plane(2, 1, h, row0 + j * KT);
+                if (j + 2 < n) {
+                    load_plane(1, 0, h, row0 + (j + 2) * KT);
+                    load_plane(1, 1, h, row0 + (j + 2) * KT);
                 }
             }
         }
-        __syncwarp();
     } else if (warp == 1) {
         // ================================================================== MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t kIdescS = umma_idesc_bf16(QT, KT, false);
-            constexpr uint32_t kIdescO = umma_idesc_bf16(QT, DK, true);
-            const uint32_t tmem_q = tmem_base + C::kQCol, tmem_o = tmem_base + C::kOCol;
-            uint32_t item_it = 0, cnt = 0, s_it = 0, p_it = 0;
-            // S[sbuf] = Q K^T over the K planes in the next ring slot; terms = 1: hi*hi only (pass 1), 3: lo*hi, hi*lo, hi*hi
-            auto do_s = [&](int terms) {
-                const uint32_t slot = cnt % kSlots, ph = (cnt / kSlots) & 1;
-                const uint32_t sbuf = s_it & 1;
-                mbar_wait(bar_kvfull + 8 * slot, ph);
-                mbar_wait(bar_sempty + 8 * sbuf, ((s_it >> 1) & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t stage_base = kv_base + slot * C::kSlotBytes;
-                const uint32_t tmem_s = tmem_base + C::kSCol + sbuf * KT;
+        constexpr uint32_t kIdescS = umma_idesc_bf16(QT, KT, false);
+        constexpr uint32_t kIdescO = umma_idesc_bf16(QT, DK, true);
+        const uint32_t tmem_q = tmem_base + C::kQCol, tmem_o = tmem_base + C::kOCol;
+        uint32_t item_it = 0, cnt = 0;
+        uint32_t se0 = 0, se1 = 0, pf0 = 0, pf1 = 0;   // per score tile: waits so far on "scores consumed" / "weights ready"
+        // S[sbuf] = Q K^T.  terms = 1: q_hi k_hi only (pass 1, one ring slot); 3: lo*hi, hi*lo, hi*hi (two slots: K hi, K lo)
+        auto do_s = [&](int terms, uint32_t sbuf, bool wait_consumed) {
+            const uint32_t slot0 = cnt % kSlots, ph0 = (cnt / kSlots) & 1;
+            const uint32_t slot1 = (cnt + 1) % kSlots, ph1 = ((cnt + 1) / kSlots) & 1;
+            mbar_wait(bar_kvfull + 8 * slot0, ph0);
+            if (terms == 3) mbar_wait(bar_kvfull + 8 * slot1, ph1);
+            if (wait_consumed) {
+                uint32_t& se = sbuf ? se1 : se0;
+                mbar_wait(bar_sempty + 8 * sbuf, se & 1);
+                ++se;
+            }
+            tc_fence_after();
+            const uint32_t k_hi = kv_base + slot0 * C::kSlotBytes, k_lo = kv_base + slot1 * C::kSlotBytes;
+            const uint32_t tmem_s = tmem_base + C::kSCol + sbuf * KT;
+            if (elect_one()) {
                 uint32_t accum = 0;
                 for (int term = 3 - terms; term < 3; ++term) {
-                    const int qa = term == 0 ? 1 : 0, kb = term == 1 ? 1 : 0;     // plane of Q, plane of K
+                    const uint32_t qcol = tmem_q + (term == 0 ? C::kQPlaneCols : 0);     // plane of Q
+                    const uint32_t kpl = term == 1 ? k_lo : k_hi;                        // plane of K
 #pragma unroll
                     for (int ks = 0; ks < DK / 16; ++ks) {
-                        const int c = ks >> 2, o = (ks & 3) * 32;
-                        const uint64_t db = umma_desc(stage_base + (kb * C::kChunks + c) * KT * 128 + o, 16, 1024);
-                        tc_mma_ts(tmem_s, tmem_q + qa * C::kQPlaneCols + ks * 8, db, kIdescS, accum);
+                        const uint64_t db = umma_desc(kpl + (ks >> 2) * KT * 128 + (ks & 3) * 32, 16, 1024);
+                        tc_mma_ts(tmem_s, qcol + ks * 8, db, kIdescS, accum);
                         accum = 1;
                     }
                 }
                 tc_commit(bar_sfull + 8 * sbuf);
-                tc_commit(bar_kvempty + 8 * slot);
-                ++cnt;
-                ++s_it;
-            };
-            for (int item = blockIdx.x; item < items; item += gridDim.x, ++item_it) {
-                int b, h, qt, n, klen;
-                decode(item, b, h, qt, n, klen);
-                mbar_wait(bar_qfull, item_it & 1);                  // this item's Q is in TMEM
+                tc_commit(bar_kvempty + 8 * slot0);
+                if (terms == 3) tc_commit(bar_kvempty + 8 * slot1);
+            }
+            __syncwarp();
+            cnt += terms == 3 ? 2 : 1;
+        };
+        for (int item = blockIdx.x; item < items; item += gridDim.x, ++item_it) {
+            int b, h, qt, n, klen;
+            decode(item, b, h, qt, n, klen);
+            mbar_wait(bar_qfull, item_it & 1);                      // this item's Q is in TMEM
+            tc_fence_after();
+            // ---- pass 1: shift = max of the hi*hi scores.  Tiles 0, 1 follow the previous item's PV products in
+            // issue order; later tiles wait until the softmax group has read the scores they overwrite.
+            for (int j = 0; j < n; ++j) do_s(1, j & 1, j >= 2);
+            // ---- pass 2: S(0), S(1) wait for the last pass-1 scores of their tile to be read; after that
+            // S(j+2) follows P(j) V(j) in issue order and needs no barrier.
+            do_s(3, 0, true);
+            if (n > 1) do_s(3, 1, true);
+            if (n <= 2) { if (elect_one()) tc_commit(bar_qempty); __syncwarp(); }   // last read of Q: the next item's Q may land
+            mbar_wait(bar_oempty, (item_it & 1) ^ 1);               // previous item's O has been read out
+            tc_fence_after();
+            for (int j = 0; j < n; ++j) {
+                const uint32_t slot0 = cnt % kSlots, ph0 = (cnt / kSlots) & 1;
+                const uint32_t slot1 = (cnt + 1) % kSlots, ph1 = ((cnt + 1) / kSlots) & 1;
+                const uint32_t pbuf = j & 1;
+                uint32_t& pf = pbuf ? pf1 : pf0;
+                mbar_wait(bar_kvfull + 8 * slot0, ph0);
+                mbar_wait(bar_kvfull + 8 * slot1, ph1);
+                mbar_wait(bar_pfull + 8 * pbuf, pf & 1);
+                ++pf;
                 tc_fence_after();
-                for (int j = 0; j < n; ++j) do_s(1);                // ---- pass 1: shift = max of the hi*hi scores
-                // ---- pass 2: S runs one tile ahead of PV
-                do_s(3);
-                if (n == 1) tc_commit(bar_qempty);                  // last read of Q: the next item's Q may land
-                mbar_wait(bar_oempty, (item_it & 1) ^ 1);           // previous item's O has been read out
-                tc_fence_after();
-                for (int j = 0; j < n; ++j, ++p_it) {
-                    if (j + 1 < n) {
-                        do_s(3);
-                        if (j + 2 == n) tc_commit(bar_qempty);
-                    }
-                    const uint32_t slot = cnt % kSlots, ph = (cnt / kSlots) & 1;
-                    const uint32_t pbuf = p_it & 1;
-                    const uint32_t v_base = kv_base + slot * C::kSlotBytes;
-                    mbar_wait(bar_kvfull + 8 * slot, ph);
-                    mbar_wait(bar_pfull + 8 * pbuf, (p_it >> 1) & 1);
-                    tc_fence_after();
-                    const uint32_t tmem_p = tmem_base + C::kPCol + pbuf * 64;
+                const uint32_t v_hi = kv_base + slot0 * C::kSlotBytes, v_lo = kv_base + slot1 * C::kSlotBytes;
+                const uint32_t tmem_p = tmem_base + C::kSCol + pbuf * KT;
+                if (elect_one()) {
                     uint32_t accum = j > 0 ? 1u : 0u;
 #pragma unroll
                     for (int term = 0; term < 3; ++term) {
-                        const int pa = term == 0 ? 1 : 0, vb = term == 1 ? 1 : 0;  // plane of P, plane of V
+                        const uint32_t pl_off = term == 0 ? 16 : 0;                      // plane of P inside each 32-column group
+                        const uint32_t vpl = term == 1 ? v_lo : v_hi;                    // plane of V
 #pragma unroll
                         for (int ks = 0; ks < KT / 16; ++ks) {
                             // A = P [128 q][16 keys] from TMEM; B = V [16 keys][DK] MN-major: 64-column chunks
                             // KT*128 B apart (LBO), 8-key groups 1024 B apart (SBO)
-                            const uint64_t db = umma_desc(v_base + vb * C::kPlaneBytes + ks * 16 * 128, KT * 128, 1024);
-                            tc_mma_ts(tmem_o, tmem_p + pa * 32 + ks * 8, db, kIdescO, accum);
+                            const uint64_t db = umma_desc(vpl + ks * 16 * 128, KT * 128, 1024);
+                            tc_mma_ts(tmem_o, tmem_p + (ks >> 1) * 32 + pl_off + (ks & 1) * 8, db, kIdescO, accum);
                             accum = 1;
                         }
                     }
-                    tc_commit(bar_pempty + 8 * pbuf);
-                    tc_commit(bar_kvempty + 8 * slot);
-                    ++cnt;
+                    tc_commit(bar_kvempty + 8 * slot0);
+                    tc_commit(bar_kvempty + 8 * slot1);
+                    if (j == n - 1) tc_commit(bar_ofull);
                 }
-                tc_commit(bar_ofull);
+                __syncwarp();
+                cnt += 2;
+                if (j + 2 < n) {
+                    do_s(3, j & 1, false);
+                    if (j + 3 == n) { if (elect_one()) tc_commit(bar_qempty); __syncwarp(); }
+                }
             }
         }
-        __syncwarp();
-    } else if (warp < 6) {
-        // ================================================================== softmax
+    } else if (warp < 10) {
+        // ================================================================== softmax (two groups of 4 warps)
+        const int grp = (warp - 2) >> 2;                            // key tiles j with (j & 1) == grp, score tile grp
         const int quarter = warp & 3;
         const int r = quarter * 32 + lane;                          // query row in the tile == TMEM lane
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-        uint32_t item_it = 0, s_it = 0, p_it = 0;
+        const uint32_t tmem_s = tmem_base + lane_addr + C::kSCol + grp * KT;
+        const uint32_t sfull = bar_sfull + 8 * grp, sempty = bar_sempty + 8 * grp, pfull = bar_pfull + 8 * grp;
+        uint32_t item_it = 0, su = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x, ++item_it) {
             int b, h, qt, n, klen;
             decode(item, b, h, qt, n, klen);
             float mx = -INFINITY;
             // ---- pass 1
-            for (int j = 0; j < n; ++j, ++s_it) {
-                const uint32_t sbuf = s_it & 1;
-                mbar_wait(bar_sfull + 8 * sbuf, (s_it >> 1) & 1);
+            for (int j = grp; j < n; j += 2, ++su) {
+                mbar_wait(sfull, su & 1);
                 tc_fence_after();
-                uint32_t s0[32], s1[32];
-                tc_ld32(tmem_base + lane_addr + C::kSCol + sbuf * KT, s0);
-                tc_ld32(tmem_base + lane_addr + C::kSCol + sbuf * KT + 32, s1);
-                tc_wait_ld();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_sempty + 8 * sbuf);
                 const int kbase = j * KT;
-                if (kbase + KT <= klen) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(s0[i]), __uint_as_float(s1[i])));
-                } else {
+                for (int c = 0; c < KT / 32; ++c) {
+                    uint32_t s[32];
+                    tc_ld32(tmem_s + c * 32, s);
+                    tc_wait_ld();
+                    if (kbase + c * 32 + 32 <= klen) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        if (kbase + i < klen) mx = fmaxf(mx, __uint_as_float(s0[i]));
-                        if (kbase + 32 + i < klen) mx = fmaxf(mx, __uint_as_float(s1[i]));
+                        for (int i = 0; i < 32; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(s[i]), __uint_as_float(s[i + 1])));
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (kbase + c * 32 + i < klen) mx = fmaxf(mx, __uint_as_float(s[i]));
                     }
                 }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(sempty);                 // these scores may be overwritten
             }
-            // ---- pass 2
+            // the two groups saw disjoint keys: exchange the row maxima (buffers alternate by item parity)
+            float* mxb = mx_smem + (item_it & 1) * 2 * QT;
+            mxb[grp * QT + r] = mx;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            mx = fmaxf(mx, mxb[(grp ^ 1) * QT + r]);
+            // ---- pass 2: scores -> weights in place, 32 keys at a time
             float lsum = 0.f;
-            for (int j = 0; j < n; ++j, ++s_it, ++p_it) {
-                const uint32_t sbuf = s_it & 1, pbuf = p_it & 1;
-                mbar_wait(bar_sfull + 8 * sbuf, (s_it >> 1) & 1);
+            for (int j = grp; j < n; j += 2, ++su) {
+                mbar_wait(sfull, su & 1);
                 tc_fence_after();
-                uint32_t s0[32], s1[32];
-                tc_ld32(tmem_base + lane_addr + C::kSCol + sbuf * KT, s0);
-                tc_ld32(tmem_base + lane_addr + C::kSCol + sbuf * KT + 32, s1);
-                tc_wait_ld();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_sempty + 8 * sbuf);
                 const int kbase = j * KT;
-                const bool full_tile = kbase + KT <= klen;
-                uint32_t hi[32], lo[32];                             // 64 keys x bf16, packed in pairs (even key in the low half)
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int half = i >> 4, w = (i & 15) * 2;       // word i covers keys 2i, 2i+1
-                    const uint32_t* src = half ? s1 : s0;
-                    float p0 = fast_exp2(__uint_as_float(src[w]) - mx);
-                    float p1 = fast_exp2(__uint_as_float(src[w + 1]) - mx);
-                    if (!full_tile) {
-                        if (kbase + 2 * i >= klen) p0 = 0.f;
-                        if (kbase + 2 * i + 1 >= klen) p1 = 0.f;
+                for (int c = 0; c < KT / 32; ++c) {
+                    uint32_t s[32];
+                    tc_ld32(tmem_s + c * 32, s);
+                    tc_wait_ld();
+                    const bool full_chunk = kbase + c * 32 + 32 <= klen;
+                    uint32_t hi[16], lo[16];                         // 32 keys x bf16, packed in pairs (even key in the low half)
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float p0 = fast_exp2(__uint_as_float(s[2 * i]) - mx);
+                        float p1 = fast_exp2(__uint_as_float(s[2 * i + 1]) - mx);
+                        if (!full_chunk) {
+                            if (kbase + c * 32 + 2 * i >= klen) p0 = 0.f;
+                            if (kbase + c * 32 + 2 * i + 1 >= klen) p1 = 0.f;
+                        }
+                        lsum += p0 + p1;
+                        split_bf16x2(p0, p1, hi[i], lo[i]);
                     }
-                    lsum += p0 + p1;
-                    split_bf16x2(p0, p1, hi[i], lo[i]);
+                    tc_st16(tmem_s + c * 32, hi);
+                    tc_st16(tmem_s + c * 32 + 16, lo);
                 }
-                mbar_wait(bar_pempty + 8 * pbuf, ((p_it >> 1) & 1) ^ 1);   // the PV that read this P buffer has retired
-                tc_fence_after();
-                const uint32_t tp = tmem_base + lane_addr + C::kPCol + pbuf * 64;
-                tc_st32(tp, hi);
-                tc_st32(tp + 32, lo);
                 tc_wait_st();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_pfull + 8 * pbuf);
+                if (lane == 0) mbar_arrive(pfull);
             }
-            // ---- hand the row sums to the epilogue warps
-            l_smem[(item_it & 1) * QT + r] = lsum;
+            // ---- hand this group's row sums to the epilogue warps
+            l_smem[((item_it & 1) * 2 + grp) * QT + r] = lsum;
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_lfull + 8 * (item_it & 1));
         }
@@ -355,7 +386,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
             mbar_wait(bar_ofull, item_it & 1);
             mbar_wait(bar_lfull + 8 * (item_it & 1), (item_it >> 1) & 1);
             tc_fence_after();
-            const float inv = 1.0f / l_smem[(item_it & 1) * QT + r];
+            const float inv = 1.0f / (l_smem[(item_it & 1) * 2 * QT + r] + l_smem[((item_it & 1) * 2 + 1) * QT + r]);
             const int row = qt * QT + r;
             const int64_t grow = (int64_t)b * p.frames + row;
 #pragma unroll 1
@@ -419,7 +450,7 @@ void launch_attention_tc(Planes qkv, int64_t plane_stride, int ld, int d_model, 
     FA_REQUIRE(ldo % 8 == 0 && ld % 8 == 0, "attention strides must be multiples of 8");
     FA_REQUIRE(qkv.lo == qkv.hi + plane_stride, "attention expects the lo plane `plane_stride` elements after the hi plane");
     const int rows = batch * frames;
-    const TcOperand mkv = tc_make_operand(qkv.hi, rows, ld, ld, plane_stride, 2, KT);     // 64-row boxes of k and v
+    const TcOperand mkv = tc_make_operand(qkv.hi, rows, ld, ld, plane_stride, 2, KT);     // 128-row boxes of k and v
     AttnParams p{};
     p.batch = batch; p.frames = frames; p.heads = heads; p.d_model = d_model; p.ld = ld; p.kv_len = kv_len;
     p.q_hi = qkv.hi; p.q_lo = qkv.lo;

@@ -234,7 +234,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     volatile uint32_t* tmem_slot_ptr =
         reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     const int m_tiles = (m + BM - 1) / BM, n_tiles = (n + BN - 1) / BN, num_tiles = m_tiles * n_tiles;
     const int k_blocks = (k + BK - 1) / BK;
 
@@ -260,7 +260,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot_ptr;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_ptr, 0);    // provably warp-uniform
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
@@ -420,7 +420,7 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
     const uint32_t tmem_slot = bar_tempty + 16;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     const int rank = (int)cluster_ctarank();                 // 0 = leader (issues the MMAs), 1 = peer
     const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
     const int k_blocks = (k + BK - 1) / BK;
@@ -447,11 +447,11 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
     tc_fence_before();
     cluster_sync_all();                           // both CTAs' barriers initialised, both TMEM allocations done
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot_ptr;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_ptr, 0);    // provably warp-uniform
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer (both CTAs)
-        if (lane == 0) {
+        {
             int stage = 0;
             uint32_t phase = 0;
             for (int u = pair; u < sched.total_units; u += num_pairs) {
@@ -464,14 +464,17 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                     const uint32_t sbase = tiles_base + stage * C::kStageBytes;
                     const uint32_t full = leader_addr(bar_full + 8 * stage);
-                    if (rank == 0) mbar_arrive_expect_tx(bar_full + 8 * stage, 2 * cta_bytes);
+                    if (elect_one()) {
+                        if (rank == 0) mbar_arrive_expect_tx(bar_full + 8 * stage, 2 * cta_bytes);
 #pragma unroll
-                    for (int p = 0; p < NP; ++p) {
-                        tma_load_3d_pair(sbase + p * kATileBytes, &map_a, full, kb * BK, a_row, p);
-                        const uint32_t wdst = sbase + NP * kATileBytes + p * C::kHalfWBytes;
-                        for (int r = 0; r < w_rows; r += 64)
-                            tma_load_3d_pair(wdst + r * BK * 2, &map_w, full, kb * BK, w_row + r, p);
+                        for (int p = 0; p < NP; ++p) {
+                            tma_load_3d_pair(sbase + p * kATileBytes, &map_a, full, kb * BK, a_row, p);
+                            const uint32_t wdst = sbase + NP * kATileBytes + p * C::kHalfWBytes;
+                            for (int r = 0; r < w_rows; r += 64)
+                                tma_load_3d_pair(wdst + r * BK * 2, &map_w, full, kb * BK, w_row + r, p);
+                        }
                     }
+                    __syncwarp();
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -479,7 +482,7 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
         __syncwarp();
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (leader CTA only)
-        if (rank == 0 && lane == 0) {
+        if (rank == 0) {
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -499,24 +502,27 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                     const uint32_t sbase = tiles_base + stage * C::kStageBytes;
                     const uint32_t a_hi = sbase, a_lo = sbase + kATileBytes;
                     const uint32_t w_hi = sbase + NP * kATileBytes, w_lo = w_hi + C::kHalfWBytes;
-                    uint32_t accum = kb > 0 ? 1u : 0u;
-                    if constexpr (NP == 2) {
+                    if (elect_one()) {
+                        uint32_t accum = kb > 0 ? 1u : 0u;
+                        if constexpr (NP == 2) {
 #pragma unroll
-                        for (int ks = 0; ks < BK / 16; ++ks) {
-                            tc_mma_pair(tmem_d, umma_desc_sw128(a_lo + ks * 32), umma_desc_sw128(w_hi + ks * 32), idesc, accum);
-                            accum = 1u;
+                            for (int ks = 0; ks < BK / 16; ++ks) {
+                                tc_mma_pair(tmem_d, umma_desc_sw128(a_lo + ks * 32), umma_desc_sw128(w_hi + ks * 32), idesc, accum);
+                                accum = 1u;
+                            }
+#pragma unroll
+                            for (int ks = 0; ks < BK / 16; ++ks)
+                                tc_mma_pair(tmem_d, umma_desc_sw128(a_hi + ks * 32), umma_desc_sw128(w_lo + ks * 32), idesc, 1u);
                         }
 #pragma unroll
-                        for (int ks = 0; ks < BK / 16; ++ks)
-                            tc_mma_pair(tmem_d, umma_desc_sw128(a_hi + ks * 32), umma_desc_sw128(w_lo + ks * 32), idesc, 1u);
+                        for (int ks = 0; ks < BK / 16; ++ks) {
+                            tc_mma_pair(tmem_d, umma_desc_sw128(a_hi + ks * 32), umma_desc_sw128(w_hi + ks * 32), idesc, accum);
+                            accum = 1u;
+                        }
+                        tc_commit_pair(bar_empty + 8 * stage);            // frees this stage in both CTAs
+                        if (kb == k_blocks - 1) tc_commit_pair(bar_tfull + 8 * acc);
                     }
-#pragma unroll
-                    for (int ks = 0; ks < BK / 16; ++ks) {
-                        tc_mma_pair(tmem_d, umma_desc_sw128(a_hi + ks * 32), umma_desc_sw128(w_hi + ks * 32), idesc, accum);
-                        accum = 1u;
-                    }
-                    tc_commit_pair(bar_empty + 8 * stage);            // frees this stage in both CTAs
-                    if (kb == k_blocks - 1) tc_commit_pair(bar_tfull + 8 * acc);
+                    __syncwarp();
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }
             }

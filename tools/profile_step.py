@@ -50,13 +50,16 @@ def main():
     torch.cuda.synchronize()
     l0 = eng.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    import time
     e0.record()
+    t0 = time.perf_counter()
     for _ in range(args.steps):
         step()
+    enqueue_ms = (time.perf_counter() - t0) * 1e3 / max(args.steps, 1)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / max(args.steps, 1)
-    print(json.dumps({"batch": args.batch, "seconds": args.seconds, "ms_per_step": ms,
+    print(json.dumps({"batch": args.batch, "seconds": args.seconds, "ms_per_step": ms, "cpu_enqueue_ms_per_step": enqueue_ms,
                       "audio_s_per_s": args.batch * args.seconds / (ms * 1e-3),
                       "launches_per_step": (eng.launch_count() - l0) // max(args.steps, 1),
                       "ids_checksum": int(ids.to(torch.int64).sum().item())}))

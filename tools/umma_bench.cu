@@ -1,0 +1,100 @@
+// Micro-benchmark (experiments only, not product code): cycles per tcgen05.mma for M128 x N x K16 bf16,
+// A from shared memory (SS) or tensor memory (TS), accumulating into one TMEM tile or alternating
+// between two.  One CTA per SM, one issuing lane.  Operands are whatever is in smem/TMEM (timing only).
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o umma_bench tools/umma_bench.cu && ./umma_bench
+#include <cstdint>
+#include <cstdio>
+#include <cuda_runtime.h>
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void mma_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+                 ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n"
+                 ::"r"(d), "r"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+
+// mode: 0 SS, 1 TS.  n: UMMA N.  alt: number of accumulators cycled through (1, 2 or 4).  kchain: MMAs per commit group.
+__global__ void __launch_bounds__(128, 1) k_bench(int mode, int n, int alt, int iters, long long* out) {
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < 64 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem_raw)[i] = 0x3c003c00u;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_slot, 0);
+    if (warp == 0) {
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint64_t da = umma_desc(base, 16, 1024), db = umma_desc(base + 16384, 16, 1024);
+        long long t0 = 0, t1 = 0;
+        if (elect_one()) {
+            t0 = clock64();
+            for (int it = 0; it < iters; ++it) {
+                const uint32_t d = tmem + (uint32_t)(it % alt) * (uint32_t)n;      // accumulators side by side
+                if (mode == 0) mma_ss(d, da, db, idesc, 1u);
+                else mma_ts(d, tmem + 448, db, idesc, 1u);
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+        }
+        __syncwarp();
+        uint32_t ok = 0;
+        while (!ok) {
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                         : "=r"(ok) : "r"(smem_u32(&bar)), "r"(0u) : "memory");
+        }
+        t1 = clock64();
+        if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) out[0] = t1 - t0;
+        long long tt = __shfl_sync(0xffffffffu, t0, 0);
+        (void)tt;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    }
+}
+
+int main() {
+    long long* d_out;
+    cudaMalloc(&d_out, 8);
+    cudaFuncSetAttribute(k_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 66 * 1024);
+    const int iters = 4096;
+    for (int warm = 0; warm < 2; ++warm)
+        for (int mode = 0; mode < 2; ++mode)
+            for (int n : {64, 128, 256})
+                for (int alt : {1, 2, 4}) {
+                    if (alt * n > 384) continue;
+                    k_bench<<<148, 128, 66 * 1024>>>(mode, n, alt, iters, d_out);
+                    cudaError_t e = cudaDeviceSynchronize();
+                    long long cyc = 0;
+                    cudaMemcpy(&cyc, d_out, 8, cudaMemcpyDeviceToHost);
+                    if (warm)
+                        printf("%s N=%3d accumulators=%d : %7.1f cycles per MMA (ideal %d) %s\n", mode ? "TS" : "SS", n, alt,
+                               (double)cyc / iters, n / 2, e == cudaSuccess ? "" : cudaGetErrorString(e));
+                }
+    return 0;
+}
