@@ -102,6 +102,10 @@ Context::Context(int device, int max_batch, int64_t max_samples, int precision)
     FA_REQUIRE(prop.major == 10, "this library is built for sm_100a (B200) only; found compute capability " +
                                      std::to_string(prop.major) + "." + std::to_string(prop.minor));
     FA_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    FA_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+    for (auto& ev : ev_up_) FA_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    FA_CUDA(cudaEventCreateWithFlags(&ev_enc_, cudaEventDisableTiming));
+    FA_CUDA(cudaEventCreateWithFlags(&ev_ad_, cudaEventDisableTiming));
     frontend_init_device();
     attention_init_device();
     tc_init_device();
@@ -124,6 +128,10 @@ Context::~Context() {
         g_rings.erase(it);
     }
     if (h_lens_) cudaFreeHost(h_lens_);
+    for (auto& ev : ev_up_) if (ev) cudaEventDestroy(ev);
+    if (ev_enc_) cudaEventDestroy(ev_enc_);
+    if (ev_ad_) cudaEventDestroy(ev_ad_);
+    if (copy_stream_) cudaStreamDestroy(copy_stream_);
     if (own_stream_ && stream_) cudaStreamDestroy(stream_);
 }
 
@@ -278,6 +286,20 @@ void Context::finalize() {
         derived_.back()->alloc(mt.size() * 4);
         FA_CUDA(cudaMemcpy(derived_.back()->p, mt.data(), mt.size() * 4, cudaMemcpyHostToDevice));
         melfb_t_ = derived_.back()->as<float>();
+        // support of each mel filter: [first, last+1) non-zero bin.  A zero weight contributes exactly 0 to the
+        // reference's dense 80 x 201 product, so the kernel only walks the support (HTK triangles are ~5 bins wide)
+        std::vector<int> range(2 * kMels);
+        for (int j = 0; j < kMels; ++j) {
+            int lo = kBins, hi = 0;
+            for (int k = 0; k < kBins; ++k)
+                if (hm[(size_t)j * kBins + k] != 0.f) { lo = std::min(lo, k); hi = std::max(hi, k + 1); }
+            if (hi <= lo) { lo = 0; hi = 0; }
+            range[2 * j] = lo; range[2 * j + 1] = hi;
+        }
+        derived_.emplace_back(new DevBuf);
+        derived_.back()->alloc(range.size() * sizeof(int));
+        FA_CUDA(cudaMemcpy(derived_.back()->p, range.data(), range.size() * sizeof(int), cudaMemcpyHostToDevice));
+        mel_range_ = derived_.back()->as<int>();
         auto it = tensors_.find("const.pos_enc");
         if (it == tensors_.end() || it->second.shape.size() != 2 || it->second.shape[1] != kDin)
             throw Error("missing or malformed tensor: const.pos_enc");
@@ -491,11 +513,7 @@ void Context::projector(const Projector& P, const Act& in, int batch, int frames
 
 // ------------------------------------------------------------------------------------ graphs
 
-void Context::encode_dev(const float* d_audio, int batch, int64_t s_phys, const int64_t* h_ilens, float* d_enc,
-                         float* d_adaptor) {
-    ensure_room(batch, s_phys);
-    set_device();
-    const int t_mel = (int)(s_phys / kHop + 1), frames = lfr_frames_of(s_phys), M = batch * frames;
+void Context::stage_lengths(int batch, int64_t s_phys, const int64_t* h_ilens) {
     LenRing& ring = g_rings[this];
     const int slot = ring.next;
     ring.next = (ring.next + 1) % kLenSlots;
@@ -510,10 +528,29 @@ void Context::encode_dev(const float* d_audio, int batch, int64_t s_phys, const 
     }
     FA_CUDA(cudaMemcpyAsync(lens_.p, hl, (size_t)3 * max_batch_ * sizeof(int), cudaMemcpyHostToDevice, stream_));
     FA_CUDA(cudaEventRecord(ring.ev[slot], stream_));
+}
 
-    launch_segment_sums(d_audio, batch, s_phys, d_nvalid_, partials_.as<double>(), stream_);
-    launch_fbank(d_audio, batch, s_phys, d_nvalid_, partials_.as<double>(), dft_t_, melfb_t_, logmel_.as<float>(), t_mel,
-                 stream_);
+// a1-a2 for segments b0 .. b0+nb-1 of the batch (segments are independent): waveform -> log-mel
+void Context::front_end(const float* d_audio, int b0, int nb, int64_t s_phys) {
+    const int t_mel = (int)(s_phys / kHop + 1);
+    double* parts = partials_.as<double>() + (size_t)b0 * kMeanParts;
+    launch_segment_sums(d_audio, nb, s_phys, d_nvalid_ + b0, parts, stream_);
+    launch_fbank(d_audio, nb, s_phys, d_nvalid_ + b0, parts, dft_t_, melfb_t_, mel_range_,
+                 logmel_.as<float>() + (size_t)b0 * t_mel * kMels, t_mel, stream_);
+}
+
+void Context::encode_dev(const float* d_audio, int batch, int64_t s_phys, const int64_t* h_ilens, float* d_enc,
+                         float* d_adaptor) {
+    ensure_room(batch, s_phys);
+    set_device();
+    stage_lengths(batch, s_phys, h_ilens);
+    front_end(d_audio, 0, batch, s_phys);
+    encoder_graph(batch, s_phys, d_enc, d_adaptor);
+}
+
+// a3 onwards: LFR + position -> 70 SAN-M layers -> enc ; adaptor -> adaptor_output
+void Context::encoder_graph(int batch, int64_t s_phys, float* d_enc, float* d_adaptor) {
+    const int t_mel = (int)(s_phys / kHop + 1), frames = lfr_frames_of(s_phys), M = batch * frames;
     tap("logmel", logmel_.as<float>(), (int64_t)batch * t_mel, kMels);
     float* lfr_raw = taps_on_ ? adaptor_out_.as<float>() : nullptr;     // borrowed scratch for the tap
     launch_lfr_embed(logmel_.as<float>(), batch, t_mel, frames, d_nvalid_, pos_enc_, x0_.as<float>(), lfr_raw, stream_);
@@ -533,10 +570,12 @@ void Context::encode_dev(const float* d_audio, int batch, int64_t s_phys, const 
     Planes encpl;
     if (!f32) encpl = Planes{encpl_.as<__nv_bfloat16>(), encpl_.as<__nv_bfloat16>() + m_max_ * kDenc};
     launch_layernorm(x, M, kDenc, tp_g_, tp_b_, 1e-5f, d_tvalid_, frames, d_enc, encpl, stream_);
+    FA_CUDA(cudaEventRecord(ev_enc_, stream_));                          // enc_output is final: a download may start
 
     Act in; in.f32 = d_enc; in.pl = encpl; in.ld = kDenc;
     projector(adaptor_, in, batch, frames, d_tvalid_);
     launch_row_keep(x, d_adaptor, batch, frames, kDllm, d_tlen_, stream_);
+    FA_CUDA(cudaEventRecord(ev_ad_, stream_));
 }
 
 void Context::ctc_dev(const float* d_enc, int batch, int frames, int32_t* d_ids) {
@@ -578,19 +617,30 @@ void Context::collapse_dev(const int32_t* d_ids, int batch, int frames, int32_t*
     launch_ctc_collapse(d_ids, batch, frames, vocab_ - 1, d_tokens, d_starts, d_counts, stream_);
 }
 
+// Host variants.  The audio goes up in groups of a few segments on the copy stream and the front end of a
+// group starts as soon as its samples have landed; enc_output goes down while the adaptor runs and
+// adaptor_output while the CTC head runs.  Pinned host buffers make all of it asynchronous; pageable
+// buffers still work (the copies then serialise on the host).
+void Context::upload_and_front_end(const float* audio_host, int nb, int64_t s_phys) {
+    const int groups = std::min<int>(8, nb);
+    for (int g = 0; g < groups; ++g) {
+        const int b0 = (int)((int64_t)nb * g / groups), b1 = (int)((int64_t)nb * (g + 1) / groups);
+        FA_CUDA(cudaMemcpyAsync(audio_.as<float>() + (size_t)b0 * s_phys, audio_host + (size_t)b0 * s_phys,
+                                (size_t)(b1 - b0) * s_phys * 4, cudaMemcpyHostToDevice, copy_stream_));
+        FA_CUDA(cudaEventRecord(ev_up_[g], copy_stream_));
+        FA_CUDA(cudaStreamWaitEvent(stream_, ev_up_[g], 0));
+        front_end(audio_.as<float>() + (size_t)b0 * s_phys, b0, b1 - b0, s_phys);
+    }
+}
+
+void Context::download_async(void* host, const void* dev, size_t bytes, cudaEvent_t after) {
+    FA_CUDA(cudaStreamWaitEvent(copy_stream_, after, 0));
+    FA_CUDA(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, copy_stream_));
+}
+
 void Context::encode_host(const float* audio, int batch, int64_t s_phys, const int64_t* ilens, float* enc,
                           float* adaptor) {
-    ensure_room(1, s_phys);
-    set_device();
-    const int frames = lfr_frames_of(s_phys);
-    for (int b0 = 0; b0 < batch; b0 += max_batch_) {
-        const int nb = std::min(max_batch_, batch - b0);
-        FA_CUDA(cudaMemcpyAsync(audio_.p, audio + (size_t)b0 * s_phys, (size_t)nb * s_phys * 4, cudaMemcpyHostToDevice, stream_));
-        encode_dev(audio_.as<float>(), nb, s_phys, ilens + b0, enc_.as<float>(), adaptor_out_.as<float>());
-        FA_CUDA(cudaMemcpyAsync(enc + (size_t)b0 * frames * kDenc, enc_.p, (size_t)nb * frames * kDenc * 4, cudaMemcpyDeviceToHost, stream_));
-        FA_CUDA(cudaMemcpyAsync(adaptor + (size_t)b0 * frames * kDllm, adaptor_out_.p, (size_t)nb * frames * kDllm * 4, cudaMemcpyDeviceToHost, stream_));
-        FA_CUDA(cudaStreamSynchronize(stream_));
-    }
+    front_half_host(audio, batch, s_phys, ilens, enc, adaptor, nullptr);
 }
 
 void Context::ctc_host(const float* enc, int batch, int frames, int32_t* ids) {
@@ -604,6 +654,7 @@ void Context::ctc_host(const float* enc, int batch, int frames, int32_t* ids) {
     }
 }
 
+// ids == nullptr: encoder session only
 void Context::front_half_host(const float* audio, int batch, int64_t s_phys, const int64_t* ilens, float* enc,
                               float* adaptor, int32_t* ids) {
     ensure_room(1, s_phys);
@@ -611,13 +662,17 @@ void Context::front_half_host(const float* audio, int batch, int64_t s_phys, con
     const int frames = lfr_frames_of(s_phys);
     for (int b0 = 0; b0 < batch; b0 += max_batch_) {
         const int nb = std::min(max_batch_, batch - b0);
-        FA_CUDA(cudaMemcpyAsync(audio_.p, audio + (size_t)b0 * s_phys, (size_t)nb * s_phys * 4, cudaMemcpyHostToDevice, stream_));
-        encode_dev(audio_.as<float>(), nb, s_phys, ilens + b0, enc_.as<float>(), adaptor_out_.as<float>());
-        if (enc) FA_CUDA(cudaMemcpyAsync(enc + (size_t)b0 * frames * kDenc, enc_.p, (size_t)nb * frames * kDenc * 4, cudaMemcpyDeviceToHost, stream_));
-        if (adaptor) FA_CUDA(cudaMemcpyAsync(adaptor + (size_t)b0 * frames * kDllm, adaptor_out_.p, (size_t)nb * frames * kDllm * 4, cudaMemcpyDeviceToHost, stream_));
-        ctc_dev(enc_.as<float>(), nb, frames, ids_.as<int32_t>());
-        FA_CUDA(cudaMemcpyAsync(ids + (size_t)b0 * frames, ids_.p, (size_t)nb * frames * 4, cudaMemcpyDeviceToHost, stream_));
+        stage_lengths(nb, s_phys, ilens + b0);
+        upload_and_front_end(audio + (size_t)b0 * s_phys, nb, s_phys);
+        encoder_graph(nb, s_phys, enc_.as<float>(), adaptor_out_.as<float>());
+        if (enc) download_async(enc + (size_t)b0 * frames * kDenc, enc_.p, (size_t)nb * frames * kDenc * 4, ev_enc_);
+        if (adaptor) download_async(adaptor + (size_t)b0 * frames * kDllm, adaptor_out_.p, (size_t)nb * frames * kDllm * 4, ev_ad_);
+        if (ids) {
+            ctc_dev(enc_.as<float>(), nb, frames, ids_.as<int32_t>());
+            FA_CUDA(cudaMemcpyAsync(ids + (size_t)b0 * frames, ids_.p, (size_t)nb * frames * 4, cudaMemcpyDeviceToHost, stream_));
+        }
         FA_CUDA(cudaStreamSynchronize(stream_));
+        FA_CUDA(cudaStreamSynchronize(copy_stream_));
     }
 }
 

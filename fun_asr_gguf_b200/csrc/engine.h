@@ -112,6 +112,12 @@ private:
     void projector(const Projector& P, const Act& in, int batch, int frames, const int* kv_len);
     void tap(const char* name, const float* d, int64_t rows, int64_t cols);
     void ensure_room(int batch, int64_t s_phys) const;
+    // encode_dev in three parts, so that the host variants can overlap copies with the front end
+    void stage_lengths(int batch, int64_t s_phys, const int64_t* h_ilens);
+    void front_end(const float* d_audio, int b0, int nb, int64_t s_phys);
+    void encoder_graph(int batch, int64_t s_phys, float* d_enc, float* d_adaptor);
+    void upload_and_front_end(const float* audio_host, int nb, int64_t s_phys);
+    void download_async(void* host, const void* dev, size_t bytes, cudaEvent_t after);
     Planes qkv_planes() const;
     Epilogue qkv_epilogue(int d_model, int heads, bool need_v_f32) const;
     Act h_act(int ld) const;
@@ -123,6 +129,8 @@ private:
     int t_mel_max_, t_max_;
     int64_t m_max_;
     cudaStream_t stream_ = nullptr;
+    cudaStream_t copy_stream_ = nullptr;      // host<->device copies of the host variants, overlapped with compute
+    cudaEvent_t ev_up_[8] = {}, ev_enc_ = nullptr, ev_ad_ = nullptr;
     bool own_stream_ = true, finalized_ = false, taps_on_ = false, simt_attention_ = true;
 
     struct HostTensor { std::vector<int64_t> shape; std::unique_ptr<DevBuf> buf; };
@@ -134,6 +142,7 @@ private:
     Projector adaptor_, ctc_;
     Linear ctc_lo_;
     const float *dft_t_ = nullptr, *melfb_t_ = nullptr, *pos_enc_ = nullptr;
+    const int* mel_range_ = nullptr;          // [80][2] support of each mel filter
     int pos_rows_ = 0;
 
     // workspace

@@ -46,7 +46,7 @@ k_segment_sums(const float* __restrict__ audio, int64_t s_phys, const int* __res
 __global__ void __launch_bounds__(kFbankThreads)
 k_fbank(const float* __restrict__ audio, int64_t s_phys, const int* __restrict__ n_valid,
         const double* __restrict__ partials, const float* __restrict__ dft_t, const float* __restrict__ melfb_t,
-        float* __restrict__ logmel, int t_mel) {
+        const int* __restrict__ mel_range, float* __restrict__ logmel, int t_mel) {
     extern __shared__ __align__(16) float smem[];
     float* y_s = smem;                       // [kYLen]
     float* ri_s = y_s + kYLen;               // [kFT][kRiLd]
@@ -78,26 +78,43 @@ k_fbank(const float* __restrict__ audio, int64_t s_phys, const int* __restrict__
     }
     __syncthreads();
 
-    // windowed DFT: thread owns output column kc (cos bins 0..200, then -sin bins 0..200)
-    if (tid < 2 * kBins) {
-        float acc[kFT];
+    // windowed DFT as a [32 frames x 400] x [400 x 402] product: thread = 4 adjacent output columns (cos bins
+    // 0..200, then -sin bins 0..200) x 8 frames.  Per 4 samples that is 4 coalesced 16-byte table loads
+    // (requested one step ahead of their use), 8 broadcast 16-byte loads of the signal and 128 FMAs.
+    constexpr int kQuads = (2 * kBins + 3) / 4;          // 101 column quads (the table is zero-padded to 416 columns)
+    if (tid < kQuads * 4) {
+        const int q = tid % kQuads, fg = tid / kQuads;
+        float acc[8][4];
 #pragma unroll
-        for (int f = 0; f < kFT; ++f) acc[f] = 0.f;
-        const float* wcol = dft_t + tid;
+        for (int f = 0; f < 8; ++f)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[f][c] = 0.f;
+        const float4* wq = reinterpret_cast<const float4*>(dft_t) + q;
+        constexpr int kLd4 = kDftLd / 4;
+        const float* ybase = y_s + fg * 8 * kHop;
+        float4 w0 = wq[0], w1 = wq[kLd4], w2 = wq[2 * kLd4], w3 = wq[3 * kLd4];
         for (int n = 0; n < kNfft; n += 4) {
-            const float w0 = wcol[(n + 0) * kDftLd], w1 = wcol[(n + 1) * kDftLd];
-            const float w2 = wcol[(n + 2) * kDftLd], w3 = wcol[(n + 3) * kDftLd];
-#pragma unroll
-            for (int f = 0; f < kFT; ++f) {
-                const float4 yv = *reinterpret_cast<const float4*>(&y_s[f * kHop + n]);
-                acc[f] = fmaf(yv.x, w0, acc[f]);
-                acc[f] = fmaf(yv.y, w1, acc[f]);
-                acc[f] = fmaf(yv.z, w2, acc[f]);
-                acc[f] = fmaf(yv.w, w3, acc[f]);
+            float4 x0 = w0, x1 = w1, x2 = w2, x3 = w3;
+            if (n + 4 < kNfft) {
+                x0 = wq[(n + 4) * kLd4]; x1 = wq[(n + 5) * kLd4]; x2 = wq[(n + 6) * kLd4]; x3 = wq[(n + 7) * kLd4];
             }
+#pragma unroll
+            for (int f = 0; f < 8; ++f) {
+                const float4 yv = *reinterpret_cast<const float4*>(&ybase[f * kHop + n]);
+                acc[f][0] = fmaf(yv.x, w0.x, acc[f][0]); acc[f][1] = fmaf(yv.x, w0.y, acc[f][1]);
+                acc[f][2] = fmaf(yv.x, w0.z, acc[f][2]); acc[f][3] = fmaf(yv.x, w0.w, acc[f][3]);
+                acc[f][0] = fmaf(yv.y, w1.x, acc[f][0]); acc[f][1] = fmaf(yv.y, w1.y, acc[f][1]);
+                acc[f][2] = fmaf(yv.y, w1.z, acc[f][2]); acc[f][3] = fmaf(yv.y, w1.w, acc[f][3]);
+                acc[f][0] = fmaf(yv.z, w2.x, acc[f][0]); acc[f][1] = fmaf(yv.z, w2.y, acc[f][1]);
+                acc[f][2] = fmaf(yv.z, w2.z, acc[f][2]); acc[f][3] = fmaf(yv.z, w2.w, acc[f][3]);
+                acc[f][0] = fmaf(yv.w, w3.x, acc[f][0]); acc[f][1] = fmaf(yv.w, w3.y, acc[f][1]);
+                acc[f][2] = fmaf(yv.w, w3.z, acc[f][2]); acc[f][3] = fmaf(yv.w, w3.w, acc[f][3]);
+            }
+            w0 = x0; w1 = x1; w2 = x2; w3 = x3;
         }
 #pragma unroll
-        for (int f = 0; f < kFT; ++f) ri_s[f * kRiLd + tid] = acc[f];
+        for (int f = 0; f < 8; ++f)
+            *reinterpret_cast<float4*>(&ri_s[(fg * 8 + f) * kRiLd + q * 4]) = make_float4(acc[f][0], acc[f][1], acc[f][2], acc[f][3]);
     }
     __syncthreads();
 
@@ -108,14 +125,25 @@ k_fbank(const float* __restrict__ audio, int64_t s_phys, const int* __restrict__
     }
     __syncthreads();
 
-    for (int i = tid; i < kFT * kMels; i += kFbankThreads) {
-        const int f = i / kMels, j = i - f * kMels;
-        if (f0 + f >= t_mel) continue;
-        float acc = 0.f;
-        const float* p = pw_s + f * kPwLd;
-#pragma unroll 3
-        for (int k = 0; k < kBins; ++k) acc = fmaf(melfb_t[k * kMels + j], p[k], acc);
-        logmel[((int64_t)b * t_mel + f0 + f) * kMels + j] = logf(__fadd_rn(acc, 1e-7f));
+    // mel + log: thread = (mel filter j, group of 8 frames); one filter weight feeds 8 independent accumulators,
+    // and only the filter's support is walked (bins in ascending order, like a dense dot product would)
+    if (tid < kMels * (kFT / 8)) {
+        const int j = tid % kMels, fg = tid / kMels;
+        const int k0 = mel_range[2 * j], k1 = mel_range[2 * j + 1];
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+        const float* p = pw_s + fg * 8 * kPwLd;
+        for (int k = k0; k < k1; ++k) {
+            const float w = melfb_t[k * kMels + j];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = fmaf(w, p[i * kPwLd + k], acc[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int f = fg * 8 + i;
+            if (f0 + f < t_mel) logmel[((int64_t)b * t_mel + f0 + f) * kMels + j] = logf(__fadd_rn(acc[i], 1e-7f));
+        }
     }
 }
 
@@ -157,9 +185,9 @@ void launch_segment_sums(const float* audio, int batch, int64_t s_phys, const in
 }
 
 void launch_fbank(const float* audio, int batch, int64_t s_phys, const int* n_valid, const double* partials,
-                  const float* dft_t, const float* melfb_t, float* logmel, int t_mel, cudaStream_t st) {
+                  const float* dft_t, const float* melfb_t, const int* mel_range, float* logmel, int t_mel, cudaStream_t st) {
     FA_LAUNCH(k_fbank, dim3(cdiv(t_mel, kFT), batch), kFbankThreads, kFbankSmem, st, audio, s_phys, n_valid, partials,
-              dft_t, melfb_t, logmel, t_mel);
+              dft_t, melfb_t, mel_range, logmel, t_mel);
 }
 
 void launch_lfr_embed(const float* logmel, int batch, int t_mel, int t_lfr, const int* n_valid, const float* pos_enc,

@@ -19,7 +19,8 @@ void launch_segment_sums(const float* audio, int batch, int64_t s_phys, const in
                          cudaStream_t st);
 // mean removal + pre-emphasis + framing + windowed DFT + power + mel + log.  logmel: [B][T_mel][80].
 void launch_fbank(const float* audio, int batch, int64_t s_phys, const int* n_valid, const double* partials,
-                  const float* dft_t /*[400][kDftLd] cos|sin transposed*/, const float* melfb /*[80][201]*/,
+                  const float* dft_t /*[400][kDftLd] cos|sin transposed*/, const float* melfb /*[201][80] transposed*/,
+                  const int* mel_range /*[80][2] first / last+1 non-zero bin of each filter*/,
                   float* logmel, int t_mel, cudaStream_t st);
 constexpr int kDftLd = 416;   // 402 real columns (201 cos + 201 -sin), padded
 // LFR stacking with replicate padding, frame mask, sqrt(512) scale and positional table.
