@@ -31,12 +31,12 @@
 //                S = Q K^T (M128 x N128) into two score tiles, O += P V (M128 x N d_k, V from smem MN-major:
 //                no transpose).  The tensor pipe executes in issue order, which is what lets S(j+2) reuse
 //                the tile P(j) lives in without a barrier: it is issued after P(j) V(j).
-//   warps 2..5   softmax group 0: even key tiles, score tile 0
-//   warps 6..9   softmax group 1: odd key tiles, score tile 1
-//                (thread = query row = TMEM lane; tcgen05.ld 32 scores, exp2 / sum, split p into hi/lo planes,
-//                tcgen05.st over the same 32 columns.  The groups exchange row maxima after pass 1 and add
-//                their row sums at the end.)
-//   warps 10..13 query loader (global -> registers -> TMEM, next item's Q while the current item finishes
+//   warps 2..17  softmax: 4 groups of 4 warps.  Group g works on key tiles j with (j & 1) == (g >> 1), score
+//                tile g >> 1, keys 64 (g & 1) .. +63 of the tile (a warp can only touch its own quarter of the
+//                TMEM lanes, so the split is by columns): thread = query row = TMEM lane; tcgen05.ld 32 scores,
+//                exp2 / sum, split p into hi/lo planes, tcgen05.st over the same 32 columns.  The groups
+//                exchange row maxima after pass 1 and their row sums are added by the epilogue.
+//   warps 18..21 query loader (global -> registers -> TMEM, next item's Q while the current item finishes
 //                its PV products) and output epilogue (O / l -> bf16 planes or fp32)
 // TMEM columns: score/weight tile 0 at 0, tile 1 at 128, O at 256, Q at 384 (hi d_k/2 | lo d_k/2).
 // Inside a score tile, keys 32c .. 32c+31 become: hi pairs in columns 32c .. +15, lo pairs in 32c+16 .. +31.
@@ -49,13 +49,13 @@ namespace {
 
 constexpr int QT = 128;          // queries per item (UMMA M)
 constexpr int KT = 128;          // keys per tile (UMMA N for S, K extent for PV)
-constexpr int kAttThreads = 448;
+constexpr int kAttThreads = 704;
 constexpr int kSlots = 6;
 
 template <int DK> struct ACfg {
     static constexpr int kChunks = DK / 64;                  // 128-byte column chunks per head row
     static constexpr int kSlotBytes = kChunks * KT * 128;    // one plane of a 128-key tile of K (or V)
-    static constexpr int kSmemBytes = kSlots * kSlotBytes + 8 * QT * 4 /*row sums and maxima*/ + 1024 + 256;
+    static constexpr int kSmemBytes = kSlots * kSlotBytes + 16 * QT * 4 /*row sums and maxima*/ + 1024 + 256;
     static constexpr uint32_t kTmemCols = 512;
     static constexpr uint32_t kSCol = 0, kOCol = 256, kQCol = 384;
     static constexpr uint32_t kQPlaneCols = DK / 2;          // packed bf16 pairs
@@ -87,8 +87,8 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t kv_base = (raw + 1023u) & ~1023u;
-    const uint32_t l_base = kv_base + kSlots * C::kSlotBytes;              // float[2 item parities][2 groups][128]: row sums, then row maxima
-    const uint32_t bars = l_base + 8 * QT * 4;
+    const uint32_t l_base = kv_base + kSlots * C::kSlotBytes;              // float[2 item parities][4 groups][128]: row sums, then row maxima
+    const uint32_t bars = l_base + 16 * QT * 4;
     const uint32_t bar_kvfull = bars, bar_kvempty = bars + 8 * kSlots;   // [kSlots] each
     const uint32_t bar_sfull = bars + 16 * kSlots, bar_sempty = bar_sfull + 16;   // [2] each
     const uint32_t bar_pfull = bar_sempty + 16;                          // [2]
@@ -98,7 +98,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
     const uint32_t tmem_slot = bar_lfull + 16;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
     float* l_smem = reinterpret_cast<float*>(smem_raw + (l_base - raw));
-    float* mx_smem = l_smem + 4 * QT;
+    float* mx_smem = l_smem + 8 * QT;
 
     const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     const int q_tiles = (p.frames + QT - 1) / QT;
@@ -107,9 +107,9 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
     if (threadIdx.x == 0) {
         for (int s = 0; s < kSlots; ++s) { mbar_init(bar_kvfull + 8 * s, 1); mbar_init(bar_kvempty + 8 * s, 1); }
         for (int s = 0; s < 2; ++s) {
-            mbar_init(bar_sfull + 8 * s, 1); mbar_init(bar_sempty + 8 * s, 4);
-            mbar_init(bar_pfull + 8 * s, 4);
-            mbar_init(bar_lfull + 8 * s, 8);
+            mbar_init(bar_sfull + 8 * s, 1); mbar_init(bar_sempty + 8 * s, 8);
+            mbar_init(bar_pfull + 8 * s, 8);
+            mbar_init(bar_lfull + 8 * s, 16);
         }
         mbar_init(bar_qfull, 4); mbar_init(bar_qempty, 1);
         mbar_init(bar_ofull, 1); mbar_init(bar_oempty, 4);
@@ -262,13 +262,14 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
                 }
             }
         }
-    } else if (warp < 10) {
-        // ================================================================== softmax (two groups of 4 warps)
-        const int grp = (warp - 2) >> 2;                            // key tiles j with (j & 1) == grp, score tile grp
+    } else if (warp < 18) {
+        // ================================================================== softmax (4 groups of 4 warps)
+        const int g4 = (warp - 2) >> 2;                             // group 0..3
+        const int grp = g4 >> 1, half = g4 & 1;                     // key tiles j with (j & 1) == grp; keys 64*half.. of the tile
         const int quarter = warp & 3;
         const int r = quarter * 32 + lane;                          // query row in the tile == TMEM lane
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-        const uint32_t tmem_s = tmem_base + lane_addr + C::kSCol + grp * KT;
+        const uint32_t tmem_s = tmem_base + lane_addr + C::kSCol + grp * KT + half * 64;
         const uint32_t sfull = bar_sfull + 8 * grp, sempty = bar_sempty + 8 * grp, pfull = bar_pfull + 8 * grp;
         uint32_t item_it = 0, su = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x, ++item_it) {
@@ -279,9 +280,9 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
             for (int j = grp; j < n; j += 2, ++su) {
                 mbar_wait(sfull, su & 1);
                 tc_fence_after();
-                const int kbase = j * KT;
+                const int kbase = j * KT + half * 64;
 #pragma unroll
-                for (int c = 0; c < KT / 32; ++c) {
+                for (int c = 0; c < 2; ++c) {
                     uint32_t s[32];
                     tc_ld32(tmem_s + c * 32, s);
                     tc_wait_ld();
@@ -298,19 +299,19 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive(sempty);                 // these scores may be overwritten
             }
-            // the two groups saw disjoint keys: exchange the row maxima (buffers alternate by item parity)
-            float* mxb = mx_smem + (item_it & 1) * 2 * QT;
-            mxb[grp * QT + r] = mx;
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            mx = fmaxf(mx, mxb[(grp ^ 1) * QT + r]);
+            // the four groups saw disjoint keys: exchange the row maxima (buffers alternate by item parity)
+            float* mxb = mx_smem + (item_it & 1) * 4 * QT;
+            mxb[g4 * QT + r] = mx;
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            mx = fmaxf(fmaxf(mxb[r], mxb[QT + r]), fmaxf(mxb[2 * QT + r], mxb[3 * QT + r]));
             // ---- pass 2: scores -> weights in place, 32 keys at a time
             float lsum = 0.f;
             for (int j = grp; j < n; j += 2, ++su) {
                 mbar_wait(sfull, su & 1);
                 tc_fence_after();
-                const int kbase = j * KT;
+                const int kbase = j * KT + half * 64;
 #pragma unroll
-                for (int c = 0; c < KT / 32; ++c) {
+                for (int c = 0; c < 2; ++c) {
                     uint32_t s[32];
                     tc_ld32(tmem_s + c * 32, s);
                     tc_wait_ld();
@@ -336,7 +337,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
                 if (lane == 0) mbar_arrive(pfull);
             }
             // ---- hand this group's row sums to the epilogue warps
-            l_smem[((item_it & 1) * 2 + grp) * QT + r] = lsum;
+            l_smem[((item_it & 1) * 4 + g4) * QT + r] = lsum;
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_lfull + 8 * (item_it & 1));
         }
@@ -386,7 +387,8 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
             mbar_wait(bar_ofull, item_it & 1);
             mbar_wait(bar_lfull + 8 * (item_it & 1), (item_it >> 1) & 1);
             tc_fence_after();
-            const float inv = 1.0f / (l_smem[(item_it & 1) * 2 * QT + r] + l_smem[((item_it & 1) * 2 + 1) * QT + r]);
+            const float* lb = l_smem + (item_it & 1) * 4 * QT + r;
+            const float inv = 1.0f / ((lb[0] + lb[QT]) + (lb[2 * QT] + lb[3 * QT]));
             const int row = qt * QT + r;
             const int64_t grow = (int64_t)b * p.frames + row;
 #pragma unroll 1

@@ -104,40 +104,68 @@ __device__ __forceinline__ void tile_coords(int tile, int m_tiles, int n_tiles, 
 // everything that touches global memory goes through a 4 KB per-warp staging tile (XOR-swizzled,
 // conflict-free both ways) so that loads and stores are row-contiguous: 8 lanes cover one 128-byte
 // line instead of 32 lanes touching 32 different lines.
-__device__ __forceinline__ void epilogue_unit(const EpiParams& ep, unsigned char* stg, int e, int lane, int m, int n,
-                                              int row0, int n0, int nw, uint32_t tmem_acc) {
+__device__ __forceinline__ void epilogue_unit(const EpiParams& ep, const CUtensorMap* map_out, const CUtensorMap* map_pl,
+                                              unsigned char* stg, bool& store_pending, int e, int lane, int m, int n, int row0,
+                                              int n0, int nw, uint32_t tmem_acc, uint32_t bar_ready, uint32_t ready_parity) {
     const int quarter = (e + 2) & 3, half = e >> 2;              // epilogue warps are warps 2..9: warp & 3 == (e + 2) & 3
     const int sub = lane >> 3, q8 = lane & 7;                    // fp32 staging: row sub+4i, 16-byte chunk q8
-    const int sub4 = lane >> 2, q4 = lane & 3;                   // bf16 staging: row sub4+8i, 16-byte chunk q4
     const int row_base = row0 + quarter * 32;
     const int row = row_base + lane;
     const uint32_t taddr = tmem_acc + ((uint32_t)(quarter * 32) << 16);
     float best = -INFINITY;
     int best_i = 0x7fffffff;
     bool any = false;
+    // residual rows of a chunk, row-contiguous (8 lanes cover one 128-byte line); requested one chunk ahead of
+    // their use — the first chunk's before the accumulator is even complete — so the loads never stall the tile
+    auto load_resid = [&](int c, float4 (&rv)[8]) {
+        const int col0 = n0 + c * 32;
+        const bool live = ep.resid && c * 32 < nw && col0 < n;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int rr = row_base + sub + 4 * i, cq = col0 + q8 * 4;
+            rv[i] = (live && rr < m && cq < n) ? *reinterpret_cast<const float4*>(ep.resid + (int64_t)rr * ep.ldr + cq)
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    const uint32_t stg_s = smem_u32(stg);
+    // the staging tile is the source of asynchronous tensor stores: before it is written again, the lane that
+    // issued the last store waits until that store has read it (it has had a whole chunk of arithmetic to do so)
+    auto stg_acquire = [&]() {
+        if (store_pending) {
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
+            store_pending = false;
+        }
+    };
+    float4 rv[8], rv_next[8];
+    load_resid(half * 4, rv);
+    mbar_wait(bar_ready, ready_parity);                          // the accumulator is complete
+    tc_fence_after();
 #pragma unroll 1
     for (int cc = 0; cc < 4; ++cc) {
         const int c = half * 4 + cc;
         const int col0 = n0 + c * 32;
         if (c * 32 >= nw || col0 >= n) break;                    // warp-uniform
         any = true;
-        // issue the global reads of this chunk before waiting on TMEM
-        float4 rv[8];
-        if (ep.resid) {
+        if (cc < 3) load_resid(c + 1, rv_next);
+        // bias of the chunk's 32 columns: the same 8 vectors for every lane (broadcast loads)
+        float bias[32];
+        if (col0 + 32 <= n) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int rr = row_base + sub + 4 * i, cq = col0 + q8 * 4;
-                rv[i] = (rr < m && cq < n) ? *reinterpret_cast<const float4*>(ep.resid + (int64_t)rr * ep.ldr + cq)
-                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < 8; ++j) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0) + j);
+                bias[4 * j] = b4.x; bias[4 * j + 1] = b4.y; bias[4 * j + 2] = b4.z; bias[4 * j + 3] = b4.w;
             }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) bias[j] = col0 + j < n ? __ldg(ep.bias + col0 + j) : 0.f;
         }
-        const float bias_l = (ep.bias && col0 + lane < n) ? ep.bias[col0 + lane] : 0.f;
         uint32_t r[32];
         tc_ld32(taddr + c * 32, r);
         tc_wait_ld();
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __fadd_rn(__uint_as_float(r[j]), __shfl_sync(0xffffffffu, bias_l, j));
+        for (int j = 0; j < 32; ++j) v[j] = __fadd_rn(__uint_as_float(r[j]), bias[j]);
         if (ep.amax_val) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
@@ -149,6 +177,7 @@ __device__ __forceinline__ void epilogue_unit(const EpiParams& ep, unsigned char
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
         }
         if (ep.resid) {
+            stg_acquire();
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int rr = sub + 4 * i;
@@ -165,27 +194,33 @@ __device__ __forceinline__ void epilogue_unit(const EpiParams& ep, unsigned char
             }
             __syncwarp();
         }
+        // Outputs leave through the staging tile as tensor stores: the tile is written in the layout the tensor
+        // map's swizzle mode expects (128-byte rows / SWIZZLE_128B for fp32, 64-byte rows / SWIZZLE_64B for a
+        // bf16 plane — also what keeps the 16-byte shared stores conflict-free), one lane issues the store, and
+        // rows or columns past the matrix edge are clipped by the map.
         if (ep.out && col0 >= ep.f32_col_begin) {
+            stg_acquire();
 #pragma unroll
             for (int j = 0; j < 8; ++j)
                 *reinterpret_cast<float4*>(stg + lane * 128 + ((j ^ (lane & 7)) * 16)) =
                     make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            fence_async_smem();
             __syncwarp();
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int rr = sub + 4 * i, cq = col0 + q8 * 4;
-                const float4 t = *reinterpret_cast<const float4*>(stg + rr * 128 + ((q8 ^ (rr & 7)) * 16));
-                if (row_base + rr < m && cq < n)
-                    *reinterpret_cast<float4*>(ep.out + (int64_t)(row_base + rr) * ep.ldc + cq) = t;
+            if (lane == 0) {
+                tma_store_2d(map_out, stg_s, col0, row_base);
+                bulk_commit();
             }
-            __syncwarp();
+            store_pending = true;
         }
         if (ep.out_hi) {
-            const float ps = col0 < ep.pl_col_scale_end ? ep.pl_col_scale : 1.0f;
+            if (col0 < ep.pl_col_scale_end) {                    // warp-uniform: the q columns of a fused q|k|v projection
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __fmul_rn(v[j], ep.pl_col_scale);
+            }
             uint32_t hw[16], lw[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-                split_bf16x2(__fmul_rn(v[2 * j], ps), __fmul_rn(v[2 * j + 1], ps), hw[j], lw[j]);
+            for (int j = 0; j < 16; ++j) split_bf16x2(v[2 * j], v[2 * j + 1], hw[j], lw[j]);
+            stg_acquire();
             // hi rows in the first 2 KB (64 B per row), lo rows in the second
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -193,19 +228,17 @@ __device__ __forceinline__ void epilogue_unit(const EpiParams& ep, unsigned char
                 *reinterpret_cast<uint4*>(stg + o) = make_uint4(hw[4 * j], hw[4 * j + 1], hw[4 * j + 2], hw[4 * j + 3]);
                 *reinterpret_cast<uint4*>(stg + 2048 + o) = make_uint4(lw[4 * j], lw[4 * j + 1], lw[4 * j + 2], lw[4 * j + 3]);
             }
+            fence_async_smem();
             __syncwarp();
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int rr = sub4 + 8 * i, cq = col0 + q4 * 8;
-                const int o = rr * 64 + ((q4 ^ ((rr >> 1) & 3)) * 16);
-                if (row_base + rr < m && cq < n) {
-                    const int64_t g = (int64_t)(row_base + rr) * ep.ldp + cq;
-                    *reinterpret_cast<uint4*>(ep.out_hi + g) = *reinterpret_cast<const uint4*>(stg + o);
-                    if (ep.out_lo) *reinterpret_cast<uint4*>(ep.out_lo + g) = *reinterpret_cast<const uint4*>(stg + 2048 + o);
-                }
+            if (lane == 0) {
+                tma_store_3d(map_pl, stg_s, col0, row_base, 0);
+                if (ep.out_lo) tma_store_3d(map_pl, stg_s + 2048, col0, row_base, 1);
+                bulk_commit();
             }
-            __syncwarp();
+            store_pending = true;
         }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rv[i] = rv_next[i];
     }
     if (ep.amax_val && any) {
         // one partial slot per (row, 128-column group): the two column halves of a 256-wide tile live in
@@ -220,7 +253,8 @@ __device__ __forceinline__ void epilogue_unit(const EpiParams& ep, unsigned char
 
 template <int NP>
 __global__ void __launch_bounds__(kThreads, 1)
-k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, int m, int n, int k,
+k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+          const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_pl, int m, int n, int k,
           int band, EpiParams ep) {
     using C = Cfg<NP>;
     extern __shared__ unsigned char smem_raw[];
@@ -331,19 +365,20 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         // ------------------------------------------------------------------ epilogue (8 warps)
         const int e = warp - 2;
         unsigned char* stg = smem_raw + (stg_base - raw) + e * 4096;
+        bool store_pending = false;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             int mt, nt;
             tile_coords(tile, m_tiles, n_tiles, band, mt, nt);
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            mbar_wait(bar_tfull + 8 * acc, acc_phase);
-            tc_fence_after();
-            epilogue_unit(ep, stg, e, lane, m, n, mt * BM, nt * BN, BN, tmem_base + acc * BN);
+            epilogue_unit(ep, &map_out, &map_pl, stg, store_pending, e, lane, m, n, mt * BM, nt * BN, BN, tmem_base + acc * BN,
+                          bar_tfull + 8 * acc, acc_phase);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
         }
+        if (lane == 0) bulk_wait_read0();                  // the staging tile must outlive the last store's read
     }
 
     tc_fence_before();
@@ -388,7 +423,9 @@ __device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
                  ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+    // relaxed: nothing in memory is being published (the TMEM reads are complete after tcgen05.wait::ld); a
+    // release at cluster scope would first drain every global store this warp has in flight
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 
 __device__ __forceinline__ void unit_coords(int u, const Sched& s, int& mt, int& n0, int& nw) {
@@ -407,7 +444,8 @@ __device__ __forceinline__ void unit_coords(int u, const Sched& s, int& mt, int&
 
 template <int NP>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-k_gemm_tc2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, int m, int n, int k,
+k_gemm_tc2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+           const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_pl, int m, int n, int k,
            Sched sched, EpiParams ep) {
     using C = Cfg2<NP>;
     extern __shared__ unsigned char smem_raw[];
@@ -532,19 +570,20 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
         // ------------------------------------------------------------------ epilogue (8 warps in each CTA)
         const int e = warp - 2;
         unsigned char* stg = smem_raw + (stg_base - raw) + e * 4096;
+        bool store_pending = false;
         int it = 0;
         for (int u = pair; u < sched.total_units; u += num_pairs, ++it) {
             int mt, n0, nw;
             unit_coords(u, sched, mt, n0, nw);
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            mbar_wait(bar_tfull + 8 * acc, acc_phase);
-            tc_fence_after();
-            epilogue_unit(ep, stg, e, lane, m, n, (mt * 2 + rank) * BM, n0, nw, tmem_base + acc * BN);
+            epilogue_unit(ep, &map_out, &map_pl, stg, store_pending, e, lane, m, n, (mt * 2 + rank) * BM, n0, nw, tmem_base + acc * BN,
+                          bar_tfull + 8 * acc, acc_phase);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(leader_addr(bar_tempty + 8 * acc));
         }
+        if (lane == 0) bulk_wait_read0();                  // the staging tile must outlive the last store's read
     }
 
     tc_fence_before();
@@ -612,6 +651,23 @@ TcOperand tc_make_operand(const __nv_bfloat16* base, int rows, int k, int64_t ro
     return op;
 }
 
+namespace {
+// tensor map of an epilogue output: `rank`-D, 32 x 32 boxes, rows of one box 128 B (fp32) or 64 B (bf16) wide
+CUtensorMap make_store_map(CUtensorMapDataType dt, int elem_bytes, void* base, int rank, const cuuint64_t* dims,
+                           const cuuint64_t* strides_bytes, CUtensorMapSwizzle swz) {
+    FA_REQUIRE(g_encode != nullptr, "tc_init_device() has not run");
+    FA_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base must be 16-byte aligned");
+    (void)elem_bytes;
+    CUtensorMap map;
+    const cuuint32_t box[3] = {32, 32, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = g_encode(&map, dt, (cuuint32_t)rank, base, dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                                CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw Error("cuTensorMapEncodeTiled (store map) failed with code " + std::to_string((int)r));
+    return map;
+}
+}  // namespace
+
 TcOperand tc_make_weight(const __nv_bfloat16* base, int rows, int k, int64_t plane_stride_elems, int planes) {
     TcOperand op = tc_make_operand(base, rows, k, k, plane_stride_elems, planes, BN);
     op.map64 = tc_make_operand(base, rows, k, k, plane_stride_elems, planes, 64).map;
@@ -647,9 +703,25 @@ void launch_gemm_tc(const TcOperand& a, const TcOperand& w, int m, int n, int k,
     FA_REQUIRE(!ep.out || (e.ldc % 4 == 0), "fp32 output stride must be a multiple of 4");
     FA_REQUIRE(!ep.resid || (e.ldr % 4 == 0), "residual stride must be a multiple of 4");
     FA_REQUIRE(!ep.out_hi || (e.ldp % 8 == 0), "plane output stride must be a multiple of 8");
-    FA_REQUIRE(!ep.amax_val || ep.bias, "fused argmax expects a bias");
+    FA_REQUIRE(ep.bias != nullptr, "the tcgen05 GEMM epilogue expects a bias vector");
+    FA_REQUIRE((reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0, "bias must be 16-byte aligned");
     FA_REQUIRE(!ep.out || n % 4 == 0, "fp32 output needs N % 4 == 0");
     FA_REQUIRE(!ep.out_hi || n % 8 == 0, "plane output needs N % 8 == 0");
+    // store maps of the epilogue outputs (unused ones are placeholders the kernel never touches)
+    CUtensorMap map_out = a.map, map_pl = a.map;
+    if (ep.out) {
+        const cuuint64_t dims[2] = {(cuuint64_t)n, (cuuint64_t)m};
+        const cuuint64_t strides[1] = {(cuuint64_t)e.ldc * 4};
+        map_out = make_store_map(CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, ep.out, 2, dims, strides, CU_TENSOR_MAP_SWIZZLE_128B);
+    }
+    if (ep.out_hi) {
+        const int planes = ep.out_lo ? 2 : 1;
+        const int64_t plane_stride = ep.out_lo ? (ep.out_lo - ep.out_hi) : (int64_t)m * e.ldp;
+        FA_REQUIRE(plane_stride > 0 && plane_stride % 8 == 0, "output planes must be hi then lo, a multiple of 8 elements apart");
+        const cuuint64_t dims[3] = {(cuuint64_t)n, (cuuint64_t)m, (cuuint64_t)planes};
+        const cuuint64_t strides[2] = {(cuuint64_t)e.ldp * 2, (cuuint64_t)plane_stride * 2};
+        map_pl = make_store_map(CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ep.out_hi, 3, dims, strides, CU_TENSOR_MAP_SWIZZLE_64B);
+    }
     prof_note_work(2.0 * m * (double)n * k, 0.0);
     // CTA pairs (256 x 256 tiles) once there is at least a full wave of them; below that the 128-row
     // tiles of the single-CTA kernel spread a small M over twice as many SMs.
@@ -664,9 +736,9 @@ void launch_gemm_tc(const TcOperand& a, const TcOperand& w, int m, int n, int k,
         s.split_log2 = (rest > 0 && 2 * rest <= pairs) ? 1 : 0;      // a last wave at most half full is cut into half tiles
         s.total_units = s.full_units + (rest << s.split_log2);
         if (n_planes == 2) {
-            FA_LAUNCH(k_gemm_tc2<2>, 2 * pairs, kThreads, Cfg2<2>::kSmemBytes, st, a.map, w.map64, m, n, k, s, ep);
+            FA_LAUNCH(k_gemm_tc2<2>, 2 * pairs, kThreads, Cfg2<2>::kSmemBytes, st, a.map, w.map64, map_out, map_pl, m, n, k, s, ep);
         } else {
-            FA_LAUNCH(k_gemm_tc2<1>, 2 * pairs, kThreads, Cfg2<1>::kSmemBytes, st, a.map, w.map64, m, n, k, s, ep);
+            FA_LAUNCH(k_gemm_tc2<1>, 2 * pairs, kThreads, Cfg2<1>::kSmemBytes, st, a.map, w.map64, map_out, map_pl, m, n, k, s, ep);
         }
         return;
     }
@@ -674,9 +746,9 @@ void launch_gemm_tc(const TcOperand& a, const TcOperand& w, int m, int n, int k,
     const int grid = tiles < g_num_sms ? tiles : g_num_sms;
     const int band = 16;
     if (n_planes == 2) {
-        FA_LAUNCH(k_gemm_tc<2>, grid, kThreads, Cfg<2>::kSmemBytes, st, a.map, w.map, m, n, k, band, ep);
+        FA_LAUNCH(k_gemm_tc<2>, grid, kThreads, Cfg<2>::kSmemBytes, st, a.map, w.map, map_out, map_pl, m, n, k, band, ep);
     } else {
-        FA_LAUNCH(k_gemm_tc<1>, grid, kThreads, Cfg<1>::kSmemBytes, st, a.map, w.map, m, n, k, band, ep);
+        FA_LAUNCH(k_gemm_tc<1>, grid, kThreads, Cfg<1>::kSmemBytes, st, a.map, w.map, map_out, map_pl, m, n, k, band, ep);
     }
 }
 

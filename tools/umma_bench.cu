@@ -25,8 +25,8 @@ __device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a, uint64_t b, uint3
                  ::"r"(d), "r"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
 
-// mode: 0 SS, 1 TS.  n: UMMA N.  alt: number of accumulators cycled through (1, 2 or 4).  kchain: MMAs per commit group.
-__global__ void __launch_bounds__(128, 1) k_bench(int mode, int n, int alt, int iters, long long* out) {
+// mode: 0 SS, 1 TS, 2 TS with MN-major B (the P V product of attn_tc.cu), 3 TS while 4 other warps stream tcgen05.ld.  n: UMMA N.  alt: number of accumulators cycled through (1, 2 or 4).  kchain: MMAs per commit group.
+__global__ void __launch_bounds__(256, 1) k_bench(int mode, int n, int alt, int iters, long long* out) {
     extern __shared__ unsigned char smem_raw[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_slot;
@@ -47,15 +47,20 @@ __global__ void __launch_bounds__(128, 1) k_bench(int mode, int n, int alt, int 
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_slot, 0);
     if (warp == 0) {
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-        const uint64_t da = umma_desc(base, 16, 1024), db = umma_desc(base + 16384, 16, 1024);
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((mode == 2 ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) |
+                               ((uint32_t)(128 >> 4) << 24);
+        const uint64_t da = umma_desc(base, 16, 1024);
+        const uint64_t db = mode == 2 ? umma_desc(base + 16384, 16384, 1024) : umma_desc(base + 16384, 16, 1024);
         long long t0 = 0, t1 = 0;
         if (elect_one()) {
             t0 = clock64();
-            for (int it = 0; it < iters; ++it) {
-                const uint32_t d = tmem + (uint32_t)(it % alt) * (uint32_t)n;      // accumulators side by side
-                if (mode == 0) mma_ss(d, da, db, idesc, 1u);
-                else mma_ts(d, tmem + 448, db, idesc, 1u);
+            const uint32_t amask = (uint32_t)alt - 1u, ta = tmem + 448;
+            if (mode == 0) {
+#pragma unroll 8
+                for (int it = 0; it < iters; ++it) mma_ss(tmem + ((uint32_t)it & amask) * (uint32_t)n, da, db, idesc, 1u);
+            } else {
+#pragma unroll 8
+                for (int it = 0; it < iters; ++it) mma_ts(tmem + ((uint32_t)it & amask) * (uint32_t)n, ta, db, idesc, 1u);
             }
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
         }
@@ -70,6 +75,75 @@ __global__ void __launch_bounds__(128, 1) k_bench(int mode, int n, int alt, int 
         long long tt = __shfl_sync(0xffffffffu, t0, 0);
         (void)tt;
     }
+    if (warp >= 4 && mode == 3) {
+        // 4 warps (one per TMEM lane quarter) read a 128-column tile over and over while the MMAs run
+        uint32_t acc = 0;
+        const uint32_t ta = tmem + ((uint32_t)((warp & 3) * 32) << 16) + 256;
+        for (int it = 0; it < iters / 4; ++it) {
+            uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
+            for (int c = 0; c < 128; c += 8) {
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                             : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7) : "r"(ta + c) : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                acc += r0 ^ r1 ^ r2 ^ r3 ^ r4 ^ r5 ^ r6 ^ r7;
+            }
+        }
+        if (acc == 0x12345u) out[1] = acc;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    }
+}
+
+// Queue depth of the tensor pipe as seen by the issuing thread: groups of `group` SS N=256 MMAs separated by a
+// dependent ALU chain of `delay` steps (~4 cycles each).  If the delay is hidden, time per group stays group*128.
+__global__ void __launch_bounds__(128, 1) k_queue(int group, int delay, int groups, long long* out) {
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < 64 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem_raw)[i] = 0x3c003c00u;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_slot, 0);
+    if (warp == 0) {
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint64_t da = umma_desc(base, 16, 1024), db = umma_desc(base + 16384, 16, 1024);
+        long long t0 = clock64();
+        uint32_t x = (uint32_t)t0;
+        for (int g = 0; g < groups; ++g) {
+            if (elect_one()) {
+#pragma unroll 4
+                for (int it = 0; it < group; ++it) mma_ss(tmem, da, db, idesc, 1u);
+            }
+            __syncwarp();
+            for (int d = 0; d < delay; ++d) x = x * 1664525u + 1013904223u;      // dependent chain, ~4-6 cycles per step
+        }
+        if (elect_one())
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+        __syncwarp();
+        uint32_t ok = 0;
+        while (!ok) {
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                         : "=r"(ok) : "r"(smem_u32(&bar)), "r"(0u) : "memory");
+        }
+        const long long t1 = clock64();
+        if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) { out[0] = t1 - t0; out[1] = x; }
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) {
@@ -80,21 +154,38 @@ __global__ void __launch_bounds__(128, 1) k_bench(int mode, int n, int alt, int 
 
 int main() {
     long long* d_out;
-    cudaMalloc(&d_out, 8);
+    cudaMalloc(&d_out, 16);
     cudaFuncSetAttribute(k_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 66 * 1024);
     const int iters = 4096;
     for (int warm = 0; warm < 2; ++warm)
-        for (int mode = 0; mode < 2; ++mode)
+        for (int mode = 0; mode < 4; ++mode)
             for (int n : {64, 128, 256})
                 for (int alt : {1, 2, 4}) {
-                    if (alt * n > 384) continue;
-                    k_bench<<<148, 128, 66 * 1024>>>(mode, n, alt, iters, d_out);
+                    if (alt * n > 256) continue;
+                    if (mode >= 2 && (alt != 1 || n == 256)) continue;
+                    k_bench<<<148, 256, 66 * 1024>>>(mode, n, alt, iters, d_out);
                     cudaError_t e = cudaDeviceSynchronize();
                     long long cyc = 0;
                     cudaMemcpy(&cyc, d_out, 8, cudaMemcpyDeviceToHost);
                     if (warm)
-                        printf("%s N=%3d accumulators=%d : %7.1f cycles per MMA (ideal %d) %s\n", mode ? "TS" : "SS", n, alt,
+                        printf("%-13s N=%3d accumulators=%d : %7.1f cycles per MMA (ideal %d) %s\n", mode == 0 ? "SS" : mode == 1 ? "TS" : mode == 2 ? "TS B=MN-major" : "TS + 4w LDTM", n, alt,
                                (double)cyc / iters, n / 2, e == cudaSuccess ? "" : cudaGetErrorString(e));
                 }
+    cudaFuncSetAttribute(k_queue, cudaFuncAttributeMaxDynamicSharedMemorySize, 66 * 1024);
+    for (int group : {1, 4, 12})
+        for (int delay : {0, 25, 50, 100, 200, 400}) {
+            const int groups = 1024;
+            long long cyc = 0, base_cyc = 0;
+            for (int rep = 0; rep < 2; ++rep) {
+                k_queue<<<148, 128, 66 * 1024>>>(group, delay, groups, d_out);
+                cudaDeviceSynchronize();
+                cudaMemcpy(&cyc, d_out, 8, cudaMemcpyDeviceToHost);
+            }
+            k_queue<<<148, 128, 66 * 1024>>>(0, delay, groups, d_out);     // the delay chain alone
+            cudaDeviceSynchronize();
+            cudaMemcpy(&base_cyc, d_out, 8, cudaMemcpyDeviceToHost);
+            printf("queue: %2d MMAs (N=256, %4d cycles) then a %6.1f-cycle chain : %7.1f cycles per group\n", group, group * 128,
+                   (double)base_cyc / groups, (double)cyc / groups);
+        }
     return 0;
 }
