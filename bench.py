@@ -256,6 +256,12 @@ def run_ours(args) -> None:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except (OSError, ValueError):
         pass
+    traffic, traffic_src = None, None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
+        traffic, traffic_src = tr["traffic_bytes_per_launch_mean"], tr["source"]
+    except (OSError, ValueError, KeyError):
+        pass
     total_ms = sum(v["ms"] for v in prof.values())
     top = max(prof.items(), key=lambda kv: kv[1]["ms"])
     gemm_name = next((k for k in prof if k.startswith("k_gemm_tc")), None) or next((k for k in prof if "gemm" in k), top[0])
@@ -268,7 +274,8 @@ def run_ours(args) -> None:
     ach = g["flops"] / (g["ms"] * 1e-3) / 1e12
     roofline = {
         "kernel": gemm_name, "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-        "traffic": None, "peak_source": peak_src,
+        "traffic": traffic, "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, mean of the four encoder-layer shapes)",
+        "traffic_source": traffic_src, "peak_source": peak_src,
         "launches_per_step": g["launches"], "avg_launch_ms": g["ms"] / g["launches"],
         "algorithmic_flops_per_step": g["flops"], "share_of_step": g["ms"] / total_ms,
         "mma_flops_factor": mma_factor, "issued_tflops": ach * mma_factor, "issued_frac": ach * mma_factor / peak_tf,
@@ -278,9 +285,9 @@ def run_ours(args) -> None:
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        v, sec, cores = oracle_rate(2, 1)
+        v, sec, cores = oracle_rate(12, 1)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"1 of the {batch} segments of a step (60 s), 2 runs after 1 warm-up, {sec:.2f} s each; torch fp32 eager port of "
+               "sample": f"1 of the {batch} segments of a step (60 s), 12 runs after 1 warm-up, {sec:.2f} s each; torch fp32 eager port of "
                          f"model_definition.py on {cpu_model()} (stand-in for ONNX Runtime CPU, which is not installable here)"}
 
     line = {
