@@ -152,6 +152,73 @@ __global__ void __launch_bounds__(128, 1) k_queue(int group, int delay, int grou
     }
 }
 
+// The issue pattern of attn_tc.cu's pass 2 without the softmax: per key tile 24 TS MMAs (N=128) into score tile
+// j&1, then 24 TS MMAs (N=128) into O whose A operand is (alias=1) the score tile written two tiles earlier —
+// the layout the kernel uses — or (alias=0) a separate TMEM region.  Ideal: 48 x 64 cycles per tile.
+template <int commits>
+__global__ void __launch_bounds__(128, 1) k_attn_pattern(int alias, int tiles, long long* out) {
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ uint64_t bar, bar2;
+    __shared__ uint32_t tmem_slot;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar2)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < 64 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem_raw)[i] = 0x3c003c00u;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_slot, 0);
+    if (warp == 0) {
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint64_t db = umma_desc(base + 16384, 16, 1024);
+        const long long t0 = clock64();
+        for (int j = 0; j < tiles; ++j) {
+            const uint32_t s_tile = tmem + (uint32_t)(j & 1) * 128u, o_tile = tmem + 256u;
+            const uint32_t p_src = alias ? s_tile : tmem + 384u;       // P(j) lives where S(j) was (alias) or elsewhere
+            if (elect_one()) {
+#pragma unroll
+                for (int i = 0; i < 24; ++i) {
+                    mma_ts(o_tile, p_src + (uint32_t)(i & 7) * 8u, db, idesc, (j | i) ? 1u : 0u);   // P(j) V(j)
+                    if (commits && (i % commits) == commits - 1)
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar2)) : "memory");
+                }
+#pragma unroll
+                for (int i = 0; i < 24; ++i) {
+                    mma_ts(s_tile, tmem + 384u + (uint32_t)(i & 7) * 8u, db, idesc, i ? 1u : 0u); // S(j+2) over the same tile
+                    if (commits && (i % commits) == commits - 1)
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar2)) : "memory");
+                }
+            }
+            __syncwarp();
+        }
+        if (elect_one())
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+        __syncwarp();
+        uint32_t ok = 0;
+        while (!ok) {
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                         : "=r"(ok) : "r"(smem_u32(&bar)), "r"(0u) : "memory");
+        }
+        const long long t1 = clock64();
+        if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) out[0] = t1 - t0;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    }
+}
+
 int main() {
     long long* d_out;
     cudaMalloc(&d_out, 16);
@@ -171,6 +238,24 @@ int main() {
                         printf("%-13s N=%3d accumulators=%d : %7.1f cycles per MMA (ideal %d) %s\n", mode == 0 ? "SS" : mode == 1 ? "TS" : mode == 2 ? "TS B=MN-major" : "TS + 4w LDTM", n, alt,
                                (double)cyc / iters, n / 2, e == cudaSuccess ? "" : cudaGetErrorString(e));
                 }
+    auto run_pattern = [&](auto kern, int commits) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 66 * 1024);
+        for (int alias : {0, 1}) {
+            long long cyc = 0;
+            for (int rep = 0; rep < 2; ++rep) {
+                kern<<<148, 128, 66 * 1024>>>(alias, 256, d_out);
+                cudaDeviceSynchronize();
+                cudaMemcpy(&cyc, d_out, 8, cudaMemcpyDeviceToHost);
+            }
+            printf("attention pattern, P %s, a commit every %2d MMAs: %7.1f cycles per key tile (ideal 3072)\n",
+                   alias ? "in place over S" : "in its own columns", commits, (double)cyc / 256);
+        }
+    };
+    run_pattern(k_attn_pattern<0>, 0);
+    run_pattern(k_attn_pattern<24>, 24);
+    run_pattern(k_attn_pattern<8>, 8);
+    run_pattern(k_attn_pattern<4>, 4);
+    run_pattern(k_attn_pattern<1>, 1);
     cudaFuncSetAttribute(k_queue, cudaFuncAttributeMaxDynamicSharedMemorySize, 66 * 1024);
     for (int group : {1, 4, 12})
         for (int delay : {0, 25, 50, 100, 200, 400}) {
