@@ -170,95 +170,137 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
         }
     } else if (warp == 1) {
         // ================================================================== MMA issuer
+        // The pipe queues only about four instructions ahead of the issuing thread (256 cycles of N = 128 work), so
+        // nothing slow may sit between the last instruction of one group of products and the first of the next:
+        // ring slots advance by increment-and-wrap, a wait that succeeds costs one instruction, and in the steady
+        // state of pass 2 the barriers of the next group are polled in the middle of issuing the current one,
+        // while the queue is full and the thread would be blocked anyway.
         constexpr uint32_t kIdescS = umma_idesc_bf16(QT, KT, false);
         constexpr uint32_t kIdescO = umma_idesc_bf16(QT, DK, true);
         const uint32_t tmem_q = tmem_base + C::kQCol, tmem_o = tmem_base + C::kOCol;
-        uint32_t item_it = 0, cnt = 0;
-        uint32_t se0 = 0, se1 = 0, pf0 = 0, pf1 = 0;   // per score tile: waits so far on "scores consumed" / "weights ready"
-        // S[sbuf] = Q K^T.  terms = 1: q_hi k_hi only (pass 1, one ring slot); 3: lo*hi, hi*lo, hi*hi (two slots: K hi, K lo)
-        auto do_s = [&](int terms, uint32_t sbuf, bool wait_consumed) {
-            const uint32_t slot0 = cnt % kSlots, ph0 = (cnt / kSlots) & 1;
-            const uint32_t slot1 = (cnt + 1) % kSlots, ph1 = ((cnt + 1) / kSlots) & 1;
-            mbar_wait(bar_kvfull + 8 * slot0, ph0);
-            if (terms == 3) mbar_wait(bar_kvfull + 8 * slot1, ph1);
-            if (wait_consumed) {
-                uint32_t& se = sbuf ? se1 : se0;
-                mbar_wait(bar_sempty + 8 * sbuf, se & 1);
-                ++se;
-            }
-            tc_fence_after();
-            const uint32_t k_hi = kv_base + slot0 * C::kSlotBytes, k_lo = kv_base + slot1 * C::kSlotBytes;
-            const uint32_t tmem_s = tmem_base + C::kSCol + sbuf * KT;
-            if (elect_one()) {
-                uint32_t accum = 0;
-                for (int term = 3 - terms; term < 3; ++term) {
-                    const uint32_t qcol = tmem_q + (term == 0 ? C::kQPlaneCols : 0);     // plane of Q
-                    const uint32_t kpl = term == 1 ? k_lo : k_hi;                        // plane of K
+        uint32_t item_it = 0;
+        uint32_t slot = 0, slot_ph = 0;                             // next ring slot and its fill parity
+        uint32_t se0 = 0, se1 = 0, pf0 = 0, pf1 = 0;                // per score tile: waits so far on "scores consumed" / "weights ready"
+        auto take = [&](uint32_t& s_out, uint32_t& ph_out) {
+            s_out = slot; ph_out = slot_ph;
+            if (++slot == kSlots) { slot = 0; slot_ph ^= 1; }
+        };
+        // one product Q(plane) K(plane)^T into the score tile: DK/16 instructions
+        auto s_term = [&](uint32_t tile, uint32_t qcol, uint32_t kpl, uint32_t first_accum) {
 #pragma unroll
-                    for (int ks = 0; ks < DK / 16; ++ks) {
-                        const uint64_t db = umma_desc(kpl + (ks >> 2) * KT * 128 + (ks & 3) * 32, 16, 1024);
-                        tc_mma_ts(tmem_s, qcol + ks * 8, db, kIdescS, accum);
-                        accum = 1;
-                    }
-                }
-                tc_commit(bar_sfull + 8 * sbuf);
-                tc_commit(bar_kvempty + 8 * slot0);
-                if (terms == 3) tc_commit(bar_kvempty + 8 * slot1);
-            }
-            __syncwarp();
-            cnt += terms == 3 ? 2 : 1;
+            for (int ks = 0; ks < DK / 16; ++ks)
+                tc_mma_ts(tile, qcol + ks * 8, umma_desc(kpl + (ks >> 2) * KT * 128 + (ks & 3) * 32, 16, 1024), kIdescS,
+                          ks ? 1u : first_accum);
+        };
+        // one product P(plane) V(plane) into O: KT/16 instructions.  A = P [128 q][16 keys] from TMEM (hi pairs at +0,
+        // lo pairs at +16 of each 32-column group); B = V [16 keys][DK] MN-major: 64-column chunks KT*128 B apart
+        // (LBO), 8-key groups 1024 B apart (SBO)
+        auto pv_term = [&](uint32_t tile, uint32_t p_off, uint32_t vpl, uint32_t first_accum) {
+#pragma unroll
+            for (int ks = 0; ks < KT / 16; ++ks)
+                tc_mma_ts(tmem_o, tile + (ks >> 1) * 32 + p_off + (ks & 1) * 8, umma_desc(vpl + ks * 16 * 128, KT * 128, 1024), kIdescO,
+                          ks ? 1u : first_accum);
         };
         for (int item = blockIdx.x; item < items; item += gridDim.x, ++item_it) {
             int b, h, qt, n, klen;
             decode(item, b, h, qt, n, klen);
             mbar_wait(bar_qfull, item_it & 1);                      // this item's Q is in TMEM
-            tc_fence_after();
-            // ---- pass 1: shift = max of the hi*hi scores.  Tiles 0, 1 follow the previous item's PV products in
-            // issue order; later tiles wait until the softmax group has read the scores they overwrite.
-            for (int j = 0; j < n; ++j) do_s(1, j & 1, j >= 2);
-            // ---- pass 2: S(0), S(1) wait for the last pass-1 scores of their tile to be read; after that
-            // S(j+2) follows P(j) V(j) in issue order and needs no barrier.
-            do_s(3, 0, true);
-            if (n > 1) do_s(3, 1, true);
-            if (n <= 2) { if (elect_one()) tc_commit(bar_qempty); __syncwarp(); }   // last read of Q: the next item's Q may land
-            mbar_wait(bar_oempty, (item_it & 1) ^ 1);               // previous item's O has been read out
-            tc_fence_after();
+            // ---- pass 1: shift = max of the hi*hi scores.  Tiles 0, 1 follow the previous item's P V in issue order;
+            // later tiles wait until the softmax group has read the scores they overwrite.
             for (int j = 0; j < n; ++j) {
-                const uint32_t slot0 = cnt % kSlots, ph0 = (cnt / kSlots) & 1;
-                const uint32_t slot1 = (cnt + 1) % kSlots, ph1 = ((cnt + 1) / kSlots) & 1;
-                const uint32_t pbuf = j & 1;
-                uint32_t& pf = pbuf ? pf1 : pf0;
-                mbar_wait(bar_kvfull + 8 * slot0, ph0);
-                mbar_wait(bar_kvfull + 8 * slot1, ph1);
-                mbar_wait(bar_pfull + 8 * pbuf, pf & 1);
-                ++pf;
+                const uint32_t buf = j & 1;
+                uint32_t s0, p0;
+                take(s0, p0);
+                mbar_wait(bar_kvfull + 8 * s0, p0);
+                if (j >= 2) { uint32_t& se = buf ? se1 : se0; mbar_wait(bar_sempty + 8 * buf, se & 1); ++se; }
                 tc_fence_after();
-                const uint32_t v_hi = kv_base + slot0 * C::kSlotBytes, v_lo = kv_base + slot1 * C::kSlotBytes;
-                const uint32_t tmem_p = tmem_base + C::kSCol + pbuf * KT;
                 if (elect_one()) {
-                    uint32_t accum = j > 0 ? 1u : 0u;
-#pragma unroll
-                    for (int term = 0; term < 3; ++term) {
-                        const uint32_t pl_off = term == 0 ? 16 : 0;                      // plane of P inside each 32-column group
-                        const uint32_t vpl = term == 1 ? v_lo : v_hi;                    // plane of V
-#pragma unroll
-                        for (int ks = 0; ks < KT / 16; ++ks) {
-                            // A = P [128 q][16 keys] from TMEM; B = V [16 keys][DK] MN-major: 64-column chunks
-                            // KT*128 B apart (LBO), 8-key groups 1024 B apart (SBO)
-                            const uint64_t db = umma_desc(vpl + ks * 16 * 128, KT * 128, 1024);
-                            tc_mma_ts(tmem_o, tmem_p + (ks >> 1) * 32 + pl_off + (ks & 1) * 8, db, kIdescO, accum);
-                            accum = 1;
-                        }
-                    }
-                    tc_commit(bar_kvempty + 8 * slot0);
-                    tc_commit(bar_kvempty + 8 * slot1);
+                    s_term(tmem_base + C::kSCol + buf * KT, tmem_q, kv_base + s0 * C::kSlotBytes, 0u);
+                    tc_commit(bar_sfull + 8 * buf);
+                    tc_commit(bar_kvempty + 8 * s0);
+                }
+                __syncwarp();
+            }
+            // ---- pass 2.  S(0), S(1) wait for the last pass-1 scores of their tile to be read; after that S(j+2)
+            // follows P(j) V(j) in issue order and needs no barrier of its own.
+            uint32_t ka, kpa, kb, kpb;                              // ring slots of the S about to be issued (K hi, K lo)
+            for (int j = 0; j < 2 && j < n; ++j) {
+                const uint32_t buf = j;
+                take(ka, kpa); take(kb, kpb);
+                mbar_wait(bar_kvfull + 8 * ka, kpa);
+                mbar_wait(bar_kvfull + 8 * kb, kpb);
+                { uint32_t& se = buf ? se1 : se0; mbar_wait(bar_sempty + 8 * buf, se & 1); ++se; }
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t tile = tmem_base + C::kSCol + buf * KT;
+                    s_term(tile, tmem_q + C::kQPlaneCols, kv_base + ka * C::kSlotBytes, 0u);
+                    s_term(tile, tmem_q, kv_base + kb * C::kSlotBytes, 1u);
+                    s_term(tile, tmem_q, kv_base + ka * C::kSlotBytes, 1u);
+                    tc_commit(bar_sfull + 8 * buf);
+                    tc_commit(bar_kvempty + 8 * ka);
+                    tc_commit(bar_kvempty + 8 * kb);
+                    if (j == n - 1) tc_commit(bar_qempty);          // last read of Q: the next item's Q may land
+                }
+                __syncwarp();
+            }
+            // barriers of P(0) V(0): V hi, V lo, the weights, a drained O
+            uint32_t va, vpa, vb, vpb;
+            take(va, vpa); take(vb, vpb);
+            mbar_wait(bar_oempty, (item_it & 1) ^ 1);
+            mbar_wait(bar_kvfull + 8 * va, vpa);
+            mbar_wait(bar_kvfull + 8 * vb, vpb);
+            mbar_wait(bar_pfull, pf0 & 1);
+            ++pf0;
+            for (int j = 0; j < n; ++j) {
+                const uint32_t buf = j & 1;
+                const uint32_t tile = tmem_base + C::kSCol + buf * KT;
+                const bool s_next = j + 2 < n, pv_next = j + 1 < n;
+                // ---- P(j) V(j); in its middle, poll the K slots of S(j+2)
+                bool k_ready = true;
+                if (s_next) { take(ka, kpa); take(kb, kpb); }
+                tc_fence_after();
+                if (elect_one()) pv_term(tile, 16, kv_base + va * C::kSlotBytes, j ? 1u : 0u);
+                __syncwarp();
+                if (s_next) k_ready = mbar_try_wait(bar_kvfull + 8 * ka, kpa) & mbar_try_wait(bar_kvfull + 8 * kb, kpb);
+                if (elect_one()) {
+                    pv_term(tile, 0, kv_base + vb * C::kSlotBytes, 1u);
+                    pv_term(tile, 0, kv_base + va * C::kSlotBytes, 1u);
+                    tc_commit(bar_kvempty + 8 * va);
+                    tc_commit(bar_kvempty + 8 * vb);
                     if (j == n - 1) tc_commit(bar_ofull);
                 }
                 __syncwarp();
-                cnt += 2;
-                if (j + 2 < n) {
-                    do_s(3, j & 1, false);
-                    if (j + 3 == n) { if (elect_one()) tc_commit(bar_qempty); __syncwarp(); }
+                // ---- S(j+2) over the tile P(j) was in; in its middle, poll the barriers of P(j+1) V(j+1)
+                bool v_ready = true;
+                const uint32_t nbuf = buf ^ 1;
+                uint32_t& pfn = nbuf ? pf1 : pf0;
+                if (pv_next) { take(va, vpa); take(vb, vpb); }
+                if (s_next) {
+                    if (!k_ready) { mbar_wait(bar_kvfull + 8 * ka, kpa); mbar_wait(bar_kvfull + 8 * kb, kpb); }
+                    tc_fence_after();
+                    if (elect_one()) s_term(tile, tmem_q + C::kQPlaneCols, kv_base + ka * C::kSlotBytes, 0u);
+                    __syncwarp();
+                    v_ready = mbar_try_wait(bar_kvfull + 8 * va, vpa) & mbar_try_wait(bar_kvfull + 8 * vb, vpb) &
+                              mbar_try_wait(bar_pfull + 8 * nbuf, pfn & 1);
+                    if (elect_one()) {
+                        s_term(tile, tmem_q, kv_base + kb * C::kSlotBytes, 1u);
+                        s_term(tile, tmem_q, kv_base + ka * C::kSlotBytes, 1u);
+                        tc_commit(bar_sfull + 8 * buf);
+                        tc_commit(bar_kvempty + 8 * ka);
+                        tc_commit(bar_kvempty + 8 * kb);
+                        if (j + 3 == n) tc_commit(bar_qempty);
+                    }
+                    __syncwarp();
+                } else {
+                    v_ready = false;
+                }
+                if (pv_next) {
+                    if (!v_ready) {
+                        mbar_wait(bar_kvfull + 8 * va, vpa);
+                        mbar_wait(bar_kvfull + 8 * vb, vpb);
+                        mbar_wait(bar_pfull + 8 * nbuf, pfn & 1);
+                    }
+                    ++pfn;
                 }
             }
         }

@@ -41,9 +41,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
+// Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU.  The retry loop (with its
+// clock reads and the diagnostic) is kept out of line so that a wait that succeeds at once costs one instruction.
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
         if (clock64() - t0 > 4000000000LL) {
@@ -52,6 +52,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             __trap();
         }
     }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
 }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
     asm volatile(
