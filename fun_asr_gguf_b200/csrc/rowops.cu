@@ -13,63 +13,75 @@ namespace {
 // rows at or past t_valid[b] are written as zeros when a length vector is given (the "sweeping"
 // multiplies at model_definition.py:210,213).
 constexpr int kLnMaxVec = 8;     // float4 per lane -> d <= 1024
+constexpr int kLnRows = 2;       // rows per warp, all loads of both rows in flight before any arithmetic
 
+template <int NV>                // float4 per lane actually needed: d <= 128 * NV
 __global__ void __launch_bounds__(256)
 k_layernorm(const float* x, int rows, int d, const float* __restrict__ gamma,
             const float* __restrict__ beta, float eps, const int* __restrict__ t_valid, int frames,
-            float* y /* may alias x: a warp reads its whole row before it writes */,
+            float* y /* may alias x: a warp reads its rows before it writes them */,
             __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo) {
-    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (row >= rows) return;
+    const int row0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * kLnRows, lane = threadIdx.x & 31;
+    if (row0 >= rows) return;
     const int nvec = d >> 2;
-    const float4* xr = reinterpret_cast<const float4*>(x + (int64_t)row * d);
-    float4 v[kLnMaxVec];
-    float s = 0.f;
+    float4 v[kLnRows][NV];
 #pragma unroll
-    for (int i = 0; i < kLnMaxVec; ++i) {
-        const int idx = lane + 32 * i;
-        v[i] = idx < nvec ? xr[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
-        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-    }
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const float mean = s / (float)d;
-    float q = 0.f;
+    for (int r = 0; r < kLnRows; ++r) {
+        const bool have = row0 + r < rows;
+        const float4* xr = reinterpret_cast<const float4*>(x + (int64_t)(row0 + r) * d);
 #pragma unroll
-    for (int i = 0; i < kLnMaxVec; ++i) {
-        if (lane + 32 * i < nvec) {
-            const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
-            q += (a * a + b * b) + (c * c + e * e);
+        for (int i = 0; i < NV; ++i) {
+            const int idx = lane + 32 * i;
+            v[r][i] = (have && idx < nvec) ? xr[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-    }
-    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-    const float rstd = 1.0f / sqrtf(q / (float)d + eps);
-    bool live = true;
-    if (t_valid) {
-        const int b = row / frames, t = row - b * frames;
-        live = t < t_valid[b];
     }
     const float4* g4 = reinterpret_cast<const float4*>(gamma);
     const float4* b4 = reinterpret_cast<const float4*>(beta);
 #pragma unroll
-    for (int i = 0; i < kLnMaxVec; ++i) {
-        const int idx = lane + 32 * i;
-        if (idx >= nvec) continue;
-        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (live) {
-            const float4 g = g4[idx], bb = b4[idx];
-            r.x = (v[i].x - mean) * rstd * g.x + bb.x;
-            r.y = (v[i].y - mean) * rstd * g.y + bb.y;
-            r.z = (v[i].z - mean) * rstd * g.z + bb.z;
-            r.w = (v[i].w - mean) * rstd * g.w + bb.w;
+    for (int r = 0; r < kLnRows; ++r) {
+        const int row = row0 + r;
+        if (row >= rows) break;
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) s += (v[r][i].x + v[r][i].y) + (v[r][i].z + v[r][i].w);
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float mean = s / (float)d;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            if (lane + 32 * i < nvec) {
+                const float a = v[r][i].x - mean, b = v[r][i].y - mean, c = v[r][i].z - mean, e = v[r][i].w - mean;
+                q += (a * a + b * b) + (c * c + e * e);
+            }
         }
-        const int64_t o = (int64_t)row * d + idx * 4;
-        if (y) *reinterpret_cast<float4*>(y + o) = r;
-        if (y_hi) {
-            uint2 h, l;
-            split_bf16x2(r.x, r.y, h.x, l.x);
-            split_bf16x2(r.z, r.w, h.y, l.y);
-            *reinterpret_cast<uint2*>(y_hi + o) = h;
-            if (y_lo) *reinterpret_cast<uint2*>(y_lo + o) = l;
+        for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        const float rstd = 1.0f / sqrtf(q / (float)d + eps);
+        bool live = true;
+        if (t_valid) {
+            const int b = row / frames, t = row - b * frames;
+            live = t < t_valid[b];
+        }
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int idx = lane + 32 * i;
+            if (idx >= nvec) continue;
+            float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live) {
+                const float4 g = g4[idx], bb = b4[idx];
+                o4.x = (v[r][i].x - mean) * rstd * g.x + bb.x;
+                o4.y = (v[r][i].y - mean) * rstd * g.y + bb.y;
+                o4.z = (v[r][i].z - mean) * rstd * g.z + bb.z;
+                o4.w = (v[r][i].w - mean) * rstd * g.w + bb.w;
+            }
+            const int64_t o = (int64_t)row * d + idx * 4;
+            if (y) *reinterpret_cast<float4*>(y + o) = o4;
+            if (y_hi) {
+                uint2 h, l;
+                split_bf16x2(o4.x, o4.y, h.x, l.x);
+                split_bf16x2(o4.z, o4.w, h.y, l.y);
+                *reinterpret_cast<uint2*>(y_hi + o) = h;
+                if (y_lo) *reinterpret_cast<uint2*>(y_lo + o) = l;
+            }
         }
     }
 }
@@ -243,8 +255,14 @@ k_ctc_collapse(const int32_t* __restrict__ ids, int frames, int blank, int32_t* 
 void launch_layernorm(const float* x, int rows, int d, const float* gamma, const float* beta, float eps,
                       const int* t_valid, int frames, float* y_f32, Planes y_pl, cudaStream_t st) {
     FA_REQUIRE(d % 4 == 0 && d <= 128 * kLnMaxVec, "layernorm width must be a multiple of 4 and <= 1024");
-    FA_LAUNCH(k_layernorm, cdiv(rows, 8), 256, 0, st, x, rows, d, gamma, beta, eps, t_valid, frames, y_f32, y_pl.hi,
-              y_pl.lo);
+    const int grid = cdiv(rows, 8 * kLnRows);
+    if (d <= 512) {
+        FA_LAUNCH(k_layernorm<4>, grid, 256, 0, st, x, rows, d, gamma, beta, eps, t_valid, frames, y_f32, y_pl.hi, y_pl.lo);
+    } else if (d <= 640) {
+        FA_LAUNCH(k_layernorm<5>, grid, 256, 0, st, x, rows, d, gamma, beta, eps, t_valid, frames, y_f32, y_pl.hi, y_pl.lo);
+    } else {
+        FA_LAUNCH(k_layernorm<8>, grid, 256, 0, st, x, rows, d, gamma, beta, eps, t_valid, frames, y_f32, y_pl.hi, y_pl.lo);
+    }
 }
 
 void launch_fsmn(const float* v, int ldv, const float* w, const int* t_valid, int batch, int frames,
