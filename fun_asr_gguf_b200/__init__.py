@@ -13,7 +13,7 @@ def __getattr__(name):
     if name == "FrontHalf":
         from .engine import FrontHalf
         return FrontHalf
-    if name == "ort_shim":
+    if name in ("ort_shim", "lookahead", "segments"):
         import importlib
-        return importlib.import_module(".ort_shim", __name__)
+        return importlib.import_module("." + name, __name__)
     raise AttributeError(name)

@@ -193,3 +193,24 @@ def test_sixty_second_segment_full_size(weights, planted_weights, consts, golden
     strict = int((ids_p[0] != blobs[f"{name}.ids_planted"]).sum())
     print(f"[sixty/planted] strict id mismatches vs reference pins: {strict}/1001, distinct ids {len(np.unique(ids_p))}")
     assert np.array_equal(ids_p[0][clear], blobs[f"{name}.ids_planted"][clear])
+
+
+def test_lookahead_long_file_matches_per_segment_calls(weights):
+    """BASELINE config 4 in small: a 150 s file cut 60 s / 4 s overlap (3 windows: 60, 60, 38 s), windows of equal
+    physical length batched together; each window must equal the single-segment call the reference's loop makes."""
+    from fun_asr_gguf_b200 import lookahead, segments
+    sr = 16000
+    engine = FrontHalf(weights, device=0, max_batch=2, max_samples=60 * sr, precision="bf16x3")
+    audio = signals.structured(150 * sr, 31).numpy()
+    res = lookahead.run_file(engine, audio)
+    windows = segments.segment_windows(audio.shape[0])
+    assert [b - a for a, b in windows] == [60 * sr, 60 * sr, 38 * sr] and all(r is not None for r in res)
+    for (a, b), r in zip(windows, res):
+        enc, ad, ids = engine.front_half(audio[None, a:b], [b - a])
+        assert np.array_equal(ids, r.ids)
+        assert np.abs(enc - r.enc_output).max() <= 1e-5 * max(np.abs(enc).max(), 1.0)
+        assert np.abs(ad - r.adaptor_output).max() <= 1e-5 * max(np.abs(ad).max(), 1.0)
+        assert r.audio_embd.shape == (engine.target_len(b - a), 1024)
+    owned = [lookahead.run_file(engine, audio[: 70 * sr], world=2, rank=k) for k in range(2)]
+    assert [x is not None for x in owned[0]] == [True, False] and [x is not None for x in owned[1]] == [False, True]
+    engine.close()

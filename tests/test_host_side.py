@@ -81,6 +81,12 @@ class _OracleEngine:
     def ctc(self, enc):
         return O.ctc_ids_batch(torch.from_numpy(enc), self.w).numpy()
 
+    max_batch = 2
+
+    def front_half(self, audio, ilens):
+        e, a = self.encode(audio, ilens)
+        return e, a, self.ctc(e)
+
 
 @pytest.fixture()
 def shim(monkeypatch, weights, consts):
@@ -136,3 +142,34 @@ def test_unmodified_reference_call_sites_run_on_the_shim(shim, weights, consts):
     text, tokens, _ = nano_ctc.decode_ctc(ids, id2token)
     want = O.greedy_collapse(ids[0], 60514)
     assert [t.start for t in tokens] == [s for _, _, s in want] and len(text) == len(want)
+
+
+def test_lookahead_prefetch_feeds_the_unchanged_sessions(shim, weights, consts):
+    """every window of a long file is computed up front in equal-length batches; the per-segment
+    session calls of the reference's loop then return those arrays, identical to computing them one by one."""
+    from fun_asr_gguf_b200 import lookahead
+    sr = 16000
+    audio = signals.structured(7 * sr - 123, 5).numpy()
+    lookahead.cache().clear()
+    n = lookahead.prefetch(audio, segment_s=2.0, overlap_s=0.5)
+    windows = segments.segment_windows(audio.shape[0], 2.0, 0.5)
+    assert n == len(windows) == 5 and windows[-1][1] - windows[-1][0] < sr          # the last window is under 1 s
+    enc_sess = shim.InferenceSession("m/Fun-ASR-Nano-Encoder-Adaptor.fp32.onnx")
+    ctc_sess = shim.InferenceSession("m/Fun-ASR-Nano-CTC.fp32.onnx")
+    hits0 = lookahead.cache().hits
+    for a, b in windows:
+        chunk = audio[a:b]
+        n_phys = lookahead.physical_samples(b - a)                                 # encode_audio pads to 1 s on the CPU provider
+        fed = np.zeros((1, 1, n_phys), np.float32)
+        fed[0, 0, :b - a] = chunk
+        e, ad = enc_sess.run(None, {"audio": fed, "ilens": np.array([b - a], np.int64)})
+        ids = ctc_sess.run(None, {"enc_output": e})[0]
+        e_o, a_o = O.encode_one(torch.from_numpy(fed[0, 0]), b - a, weights, consts)
+        assert np.array_equal(e[0], e_o.numpy()) and np.array_equal(ad[0], a_o.numpy())
+        assert np.array_equal(ids[0], O.ctc_ids_one(e_o, weights).numpy())
+    assert lookahead.cache().hits - hits0 == 2 * len(windows)                      # every call was served from the cache
+    # a segment that was not prefetched still computes
+    other = signals.white(sr, 9).numpy().reshape(1, 1, -1)
+    e2 = enc_sess.run(None, {"audio": other, "ilens": np.array([sr], np.int64)})[0]
+    assert e2.shape == (1, 17, 512) and lookahead.cache().hits - hits0 == 2 * len(windows)
+    lookahead.cache().clear()
