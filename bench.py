@@ -260,10 +260,11 @@ def run_ours(args) -> None:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except (OSError, ValueError):
         pass
-    traffic, traffic_src = None, None
+    traffic, traffic_src, ncu_pipe = None, None, None
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
         traffic, traffic_src = tr["traffic_bytes_per_launch_mean"], tr["source"]
+        ncu_pipe = tr.get("tensor_pipe_active_pct_time_weighted")
     except (OSError, ValueError, KeyError):
         pass
     total_ms = sum(v["ms"] for v in prof.values())
@@ -279,7 +280,7 @@ def run_ours(args) -> None:
     roofline = {
         "kernel": gemm_name, "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
         "traffic": traffic, "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, mean of the four encoder-layer shapes)",
-        "traffic_source": traffic_src, "peak_source": peak_src,
+        "traffic_source": traffic_src, "ncu_tensor_pipe_active_pct": ncu_pipe, "peak_source": peak_src,
         "launches_per_step": g["launches"], "avg_launch_ms": g["ms"] / g["launches"],
         "algorithmic_flops_per_step": g["flops"], "share_of_step": g["ms"] / total_ms,
         "mma_flops_factor": mma_factor, "issued_tflops": ach * mma_factor, "issued_frac": ach * mma_factor / peak_tf,

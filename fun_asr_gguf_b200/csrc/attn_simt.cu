@@ -27,6 +27,7 @@ __global__ void __launch_bounds__(256)
 k_attention_simt(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, int ld,
                  int frames, const int* __restrict__ kv_len, float* __restrict__ ctx,
                  __nv_bfloat16* __restrict__ ctx_hi, __nv_bfloat16* __restrict__ ctx_lo, int ldo, float scale) {
+    grid_dependency_wait();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     AttnSmem<DK>& s = *reinterpret_cast<AttnSmem<DK>*>(smem_raw);
     constexpr int DV = DK / 4;            // float4 per head row

@@ -122,6 +122,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_ptr, 0);    // provably warp-uniform
+    grid_dependency_wait();                       // everything above overlapped the previous kernel's tail
 
     // item -> (segment b, head h, query tile qt); key tiles n
     auto decode = [&](int item, int& b, int& h, int& qt, int& n, int& klen) {

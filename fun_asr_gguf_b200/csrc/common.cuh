@@ -43,14 +43,32 @@ extern thread_local bool g_prof_on;
 void prof_before(const char* kernel, cudaStream_t st);
 void prof_after(cudaStream_t st);
 void prof_note_work(double flops, double bytes);   // algorithmic work of the next launch
-#define FA_LAUNCH(kernel, grid, block, smem, stream, ...)            \
-    do {                                                             \
-        if (::fa::g_prof_on) ::fa::prof_before(#kernel, (stream));   \
-        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);  \
-        ++::fa::g_launches;                                          \
-        if (::fa::g_prof_on) ::fa::prof_after((stream));             \
-        FA_CUDA(cudaGetLastError());                                 \
+// Every launch carries the programmatic-stream-serialization attribute: the next kernel's CTAs may be placed
+// and run their prologue (barrier init, TMEM allocation, descriptor prefetch) while the previous kernel drains;
+// each kernel calls grid_dependency_wait() before it touches global memory.  FUNASR_B200_PDL=0 turns it off.
+extern bool g_pdl;
+template <class... KArgs, class... Args>
+inline void launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &at; cfg.numAttrs = g_pdl ? 1 : 0;
+    FA_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+}
+#define FA_LAUNCH(kernel, grid, block, smem, stream, ...)                                        \
+    do {                                                                                         \
+        if (::fa::g_prof_on) ::fa::prof_before(#kernel, (stream));                               \
+        ::fa::launch_ex(kernel, dim3(grid), dim3(block), (size_t)(smem), (stream), __VA_ARGS__); \
+        ++::fa::g_launches;                                                                      \
+        if (::fa::g_prof_on) ::fa::prof_after((stream));                                         \
     } while (0)
+
+#ifdef __CUDACC__
+// Wait until the kernels this launch depends on have completed and their writes are visible (no-op without PDL).
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
 
 // bf16 "planes": a fp32 value v is carried as hi = bf16(v), lo = bf16(v - hi).  hi+lo keeps
 // 16 mantissa bits, and the three products hi*hi + hi*lo + lo*hi on the tensor cores

@@ -16,6 +16,7 @@ namespace fa {
 
 thread_local int64_t g_launches = 0;
 thread_local bool g_prof_on = false;
+bool g_pdl = [] { const char* s = getenv("FUNASR_B200_PDL"); return !(s && s[0] == '0'); }();
 
 namespace {
 struct ProfRec { std::string name; cudaEvent_t a, b; double flops, bytes; };

@@ -25,6 +25,7 @@ constexpr size_t kFbankSmem = sizeof(float) * (kYLen + kFT * kRiLd + kFT * kPwLd
 __global__ void __launch_bounds__(256)
 k_segment_sums(const float* __restrict__ audio, int64_t s_phys, const int* __restrict__ n_valid,
                double* __restrict__ partials) {
+    grid_dependency_wait();
     const int b = blockIdx.y, part = blockIdx.x;
     const int nv = n_valid[b];
     const int64_t chunk = (nv + kMeanParts - 1) / kMeanParts;
@@ -47,6 +48,7 @@ __global__ void __launch_bounds__(kFbankThreads)
 k_fbank(const float* __restrict__ audio, int64_t s_phys, const int* __restrict__ n_valid,
         const double* __restrict__ partials, const float* __restrict__ dft_t, const float* __restrict__ melfb_t,
         const int* __restrict__ mel_range, float* __restrict__ logmel, int t_mel) {
+    grid_dependency_wait();
     extern __shared__ __align__(16) float smem[];
     float* y_s = smem;                       // [kYLen]
     float* ri_s = y_s + kYLen;               // [kFT][kRiLd]
@@ -150,6 +152,7 @@ k_fbank(const float* __restrict__ audio, int64_t s_phys, const int* __restrict__
 __global__ void __launch_bounds__(160)
 k_lfr_embed(const float* __restrict__ logmel, int t_mel, int t_lfr, const int* __restrict__ n_valid,
             const float* __restrict__ pos_enc, float* __restrict__ x0, float* __restrict__ lfr_raw) {
+    grid_dependency_wait();
     const int t = blockIdx.x, b = blockIdx.y, c4 = threadIdx.x;
     if (c4 >= kDin / 4) return;
     const int nv = n_valid[b];

@@ -17,6 +17,7 @@ __global__ void __launch_bounds__(256)
 k_gemm_simt(const float* __restrict__ a, int lda, const float* __restrict__ w, int m, int n, int k,
             const float* __restrict__ bias, const float* resid, int ldr, int relu, float* out, int ldc,
             __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, int ldp) {
+    grid_dependency_wait();
     __shared__ __align__(16) float As[BK][LDS_];
     __shared__ __align__(16) float Bs[BK][LDS_];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;

@@ -295,6 +295,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_ptr, 0);    // provably warp-uniform
+    grid_dependency_wait();                       // everything above overlapped the previous kernel's tail
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
@@ -486,6 +487,7 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
     cluster_sync_all();                           // both CTAs' barriers initialised, both TMEM allocations done
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_ptr, 0);    // provably warp-uniform
+    grid_dependency_wait();                       // everything above overlapped the previous kernel's tail
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer (both CTAs)

@@ -21,6 +21,7 @@ k_layernorm(const float* x, int rows, int d, const float* __restrict__ gamma,
             const float* __restrict__ beta, float eps, const int* __restrict__ t_valid, int frames,
             float* y /* may alias x: a warp reads its rows before it writes them */,
             __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo) {
+    grid_dependency_wait();
     const int row0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * kLnRows, lane = threadIdx.x & 31;
     if (row0 >= rows) return;
     const int nvec = d >> 2;
@@ -98,6 +99,7 @@ constexpr int kFsmnT = 8;
 __global__ void __launch_bounds__(kDenc / 4)
 k_fsmn(const float* __restrict__ v, int ldv, const float* __restrict__ w, const int* __restrict__ t_valid,
        int frames, const float* resid, float* out) {
+    grid_dependency_wait();
     const int c = threadIdx.x * 4, b = blockIdx.y, t0 = blockIdx.x * kFsmnT;
     const int tv = t_valid[b];
     const float* vb = v + (int64_t)b * frames * ldv + c;
@@ -146,6 +148,7 @@ k_fsmn(const float* __restrict__ v, int ldv, const float* __restrict__ w, const 
 __global__ void __launch_bounds__(256)
 k_row_keep(const float4* __restrict__ in, float4* __restrict__ out, int frames, int d4, const int* __restrict__ keep,
            int64_t total4) {
+    grid_dependency_wait();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total4) return;
     const int64_t row = i / d4;
@@ -155,6 +158,7 @@ k_row_keep(const float4* __restrict__ in, float4* __restrict__ out, int frames, 
 
 __global__ void __launch_bounds__(256)
 k_split_planes(const float4* __restrict__ x, int64_t n4, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+    grid_dependency_wait();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
     const float4 v = x[i];
@@ -173,6 +177,7 @@ __device__ __forceinline__ void amax_merge(float& bv, int& bi, float v, int i) {
 
 __global__ void __launch_bounds__(256)
 k_argmax_rows(const float* __restrict__ logits, int n, int ld, int32_t* __restrict__ ids) {
+    grid_dependency_wait();
     const int row = blockIdx.x;
     const float* p = logits + (int64_t)row * ld;
     float bv = -INFINITY;
@@ -196,6 +201,7 @@ k_argmax_rows(const float* __restrict__ logits, int n, int ld, int32_t* __restri
 __global__ void __launch_bounds__(256)
 k_argmax_combine(const float* __restrict__ pmax, const int32_t* __restrict__ pidx, int rows, int tiles,
                  int32_t* __restrict__ ids) {
+    grid_dependency_wait();
     // one warp per row: lanes stride over the tiles, then merge (value desc, index asc)
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -216,6 +222,7 @@ k_argmax_combine(const float* __restrict__ pmax, const int32_t* __restrict__ pid
 __global__ void __launch_bounds__(1024)
 k_ctc_collapse(const int32_t* __restrict__ ids, int frames, int blank, int32_t* __restrict__ tokens,
                int32_t* __restrict__ starts, int32_t* __restrict__ counts) {
+    grid_dependency_wait();
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int32_t* p = ids + (int64_t)b * frames;
     __shared__ int warp_tot[32];
