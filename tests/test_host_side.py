@@ -173,3 +173,31 @@ def test_lookahead_prefetch_feeds_the_unchanged_sessions(shim, weights, consts):
     e2 = enc_sess.run(None, {"audio": other, "ilens": np.array([sr], np.int64)})[0]
     assert e2.shape == (1, 17, 512) and lookahead.cache().hits - hits0 == 2 * len(windows)
     lookahead.cache().clear()
+
+
+def test_checkpoint_key_mapping_follows_load_weights(weights, monkeypatch):
+    """load_checkpoint applies HybridSenseVoice.load_weights' mapping (model_definition.py:231-238): the three module
+    prefixes pass through, ctc.ctc_lo.* becomes ctc_proj.ctc_lo.*, everything else (the LLM, the tokenizer
+    embeddings) is ignored; a missing or mis-shaped tensor is an error, not a silent random init."""
+    sd = {}
+    for k, v in weights.items():
+        sd[k.replace("ctc_proj.ctc_lo", "ctc.ctc_lo")] = v
+    for k in ("ctc.ctc_lo.bias", "audio_adaptor.blocks.1.norm2.weight"):
+        sd[k] = sd[k].to(torch.float64)                                            # dtype is normalised to fp32
+    sd["llm.model.embed_tokens.weight"] = torch.zeros(4, 4)
+    sd["ctc.ctc_lo.extra"] = torch.zeros(1)
+    monkeypatch.setattr(torch, "load", lambda path, map_location=None: {"state_dict": sd})
+    got = Wm.load_checkpoint("model.pt")
+    assert set(got) == set(weights)
+    for k in ("audio_encoder.encoders0.0.self_attn.linear_q_k_v.weight", "ctc_proj.ctc_lo.bias", "audio_adaptor.blocks.1.norm2.weight"):
+        assert got[k].dtype == torch.float32 and torch.equal(got[k], weights[k])
+    bad = dict(sd)
+    del bad["audio_encoder.tp_norm.bias"]
+    monkeypatch.setattr(torch, "load", lambda path, map_location=None: bad)
+    with pytest.raises(KeyError):
+        Wm.load_checkpoint("model.pt")
+    bad = dict(sd)
+    bad["ctc.ctc_lo.weight"] = torch.zeros(10, 512)
+    monkeypatch.setattr(torch, "load", lambda path, map_location=None: bad)
+    with pytest.raises(ValueError):
+        Wm.load_checkpoint("model.pt")
