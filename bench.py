@@ -298,8 +298,8 @@ def run_ours(args) -> None:
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {"bf16x3": "bf16x3 (bf16 hi+lo planes on tcgen05, fp32 accumulate; fp32 attention/row kernels)",
-                  "bf16": "bf16 (tcgen05, fp32 accumulate)", "fp32": "f32"}[args.precision],
+        "dtype": {"bf16x3": "bf16x3 (projections and attention: bf16 hi+lo planes on tcgen05, 3 MMAs per product, fp32 accumulate; fp32 softmax, LayerNorm, FSMN, front end)",
+                  "bf16": "bf16 (projections plain bf16 on tcgen05, attention bf16x3, fp32 accumulate; speed mode, not token-exact)", "fp32": "f32"}[args.precision],
         "data": "synthetic (0.1*N(0,1) clipped, seed 1234+i); random-init weights of the architecture (no checkpoint ships)",
         "config": {"workload": WORKLOAD, "segments_per_step_per_gpu": batch, "segment_s": SEG_S, "frames_per_segment": t,
                    "precision": args.precision, "parallelism": f"segment-dp{world}",
