@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(128, 1) k_attn_pattern(int alias, int tiles, l
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar2)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < 64 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem_raw)[i] = 0x3c003c00u;
+    for (int i = threadIdx.x; i < 66 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem_raw)[i] = 0x3c003c00u;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u) : "memory");
@@ -180,10 +180,25 @@ __global__ void __launch_bounds__(128, 1) k_attn_pattern(int alias, int tiles, l
     if (warp == 0) {
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const uint64_t db = umma_desc(base + 16384, 16, 1024);
+        const uint32_t idesc_mn = idesc | (1u << 16);
         const long long t0 = clock64();
         for (int j = 0; j < tiles; ++j) {
             const uint32_t s_tile = tmem + (uint32_t)(j & 1) * 128u, o_tile = tmem + 256u;
             const uint32_t p_src = alias ? s_tile : tmem + 384u;       // P(j) lives where S(j) was (alias) or elsewhere
+            if (alias == 2) {                                          // as attn_tc.cu: V MN-major, 16-key steps of 2048 B, two 64-column chunks 16 KB apart
+                if (elect_one()) {
+#pragma unroll
+                    for (int i = 0; i < 24; ++i)
+                        mma_ts(o_tile, s_tile + (uint32_t)((i & 7) >> 1) * 32u + (uint32_t)(i & 1) * 8u,
+                               umma_desc(base + (uint32_t)(i & 7) * 2048u, 16384, 1024), idesc_mn, (j | i) ? 1u : 0u);
+#pragma unroll
+                    for (int i = 0; i < 24; ++i)
+                        mma_ts(s_tile, tmem + 384u + (uint32_t)(i & 7) * 8u,
+                               umma_desc(base + 32768 + (uint32_t)((i & 7) >> 2) * 16384u + (uint32_t)(i & 3) * 32u, 16, 1024), idesc, i ? 1u : 0u);
+                }
+                __syncwarp();
+                continue;
+            }
             if (elect_one()) {
 #pragma unroll
                 for (int i = 0; i < 24; ++i) {
@@ -240,7 +255,7 @@ int main() {
                 }
     auto run_pattern = [&](auto kern, int commits) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 66 * 1024);
-        for (int alias : {0, 1}) {
+        for (int alias : {0, 1, 2}) {
             long long cyc = 0;
             for (int rep = 0; rep < 2; ++rep) {
                 kern<<<148, 128, 66 * 1024>>>(alias, 256, d_out);
@@ -248,7 +263,7 @@ int main() {
                 cudaMemcpy(&cyc, d_out, 8, cudaMemcpyDeviceToHost);
             }
             printf("attention pattern, P %s, a commit every %2d MMAs: %7.1f cycles per key tile (ideal 3072)\n",
-                   alias ? "in place over S" : "in its own columns", commits, (double)cyc / 256);
+                   alias == 2 ? "in place, V MN-major stepping as attn_tc.cu" : alias ? "in place over S" : "in its own columns", commits, (double)cyc / 256);
         }
     };
     run_pattern(k_attn_pattern<0>, 0);
