@@ -214,3 +214,32 @@ def test_lookahead_long_file_matches_per_segment_calls(weights):
     owned = [lookahead.run_file(engine, audio[: 70 * sr], world=2, rank=k) for k in range(2)]
     assert [x is not None for x in owned[0]] == [True, False] and [x is not None for x in owned[1]] == [False, True]
     engine.close()
+
+
+def test_config3_full_size_mixed_length_batch(weights, planted_weights, consts):
+    """BASELINE config 3 at full size: 32 items, lengths randint(80 000, 960 001) from seed 1234, each
+    zero-padded to the batch maximum.  Every row must be bit-identical to the same row run alone at the same physical
+    length (the CTA-pair GEMM, 128-key attention tiles and partial query tiles all change shape between the two),
+    and the rows checked against the oracle must agree within the stated tolerance with token-exact ids outside
+    near-ties.  The planted CTC projection makes the ids vary."""
+    g = torch.Generator().manual_seed(1234)
+    lens = [int(v) for v in torch.randint(80_000, 960_001, (32,), generator=g)]
+    s_phys = max(lens)
+    batch = torch.stack([signals.padded(signals.structured(n, 100 + i), s_phys) for i, n in enumerate(lens)])
+    eng = FrontHalf(planted_weights, device=0, max_batch=32, max_samples=s_phys, precision="bf16x3")
+    enc, ad, ids = eng.front_half(batch.numpy(), lens)
+    t = eng.frames(s_phys)
+    assert enc.shape == (32, t, 512) and ids.shape == (32, t)
+    for b, n in enumerate(lens):
+        tv, tl = eng.frames(n), eng.target_len(n)
+        assert not enc[b, tv:].any() and not ad[b, tl:].any()                  # masks and length control
+    for b in (0, 7, 19, 31):                                                    # batching does not change a row
+        e1, a1, i1 = eng.front_half(batch.numpy()[b:b + 1], lens[b:b + 1])
+        assert np.array_equal(e1[0], enc[b]) and np.array_equal(a1[0], ad[b]) and np.array_equal(i1[0], ids[b])
+    shortest, longest = int(np.argmin(lens)), int(np.argmax(lens))
+    for b in (shortest, longest):
+        enc_o, ad_o = O.encode_one(batch[b], lens[b], planted_weights, consts)
+        assert np.abs(enc[b] - enc_o.numpy()).max() <= ACT_TOL["bf16x3"]
+        assert np.abs(ad[b] - ad_o.numpy()).max() <= ACT_TOL["bf16x3"]
+        _check_ids(ids[b], O.ctc_logits_one(enc_o, planted_weights), "bf16x3", f"config3 row{b}")
+    eng.close()
