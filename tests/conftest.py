@@ -13,6 +13,10 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # the C-ABI library is a build artefact (git-ignored): make sure it exists and matches the sources before any
+    # test dlopens it.  A no-op when the stamp is current; nvcc cross-compiles sm_100a without a GPU.
+    from fun_asr_gguf_b200 import build as _build
+    _build.build()
 
 
 @pytest.fixture(scope="session")
