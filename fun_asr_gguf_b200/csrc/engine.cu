@@ -260,6 +260,16 @@ void Context::finalize() {
             throw Error("missing or malformed tensor: ctc_proj.ctc_lo.weight");
         vocab_ = (int)it->second.shape[0];
         ctc_lo_ = make_linear("ctc_proj.ctc_lo", vocab_, kDenc);
+        // FUNASR_B200_VOCAB=full keeps the three-product projection with the fused running argmax (comparison aid)
+        const char* vm = getenv("FUNASR_B200_VOCAB");
+        vocab_rescore_ = prec_ == kBf16x3 && !(vm && std::string(vm) == "full");
+        if (vocab_rescore_) {
+            DevBuf nm;
+            nm.alloc(sizeof(float));
+            launch_row_norm_max(ctc_lo_.w, vocab_, kDenc, nm.as<float>(), stream_);
+            FA_CUDA(cudaMemcpyAsync(&vocab_wnorm_, nm.p, sizeof(float), cudaMemcpyDeviceToHost, stream_));
+            FA_CUDA(cudaStreamSynchronize(stream_));
+        }
     }
 
     // ---- front-end constants: DFT kernels transposed to [n][cos|sin] and the mel matrix to [bin][mel]
@@ -331,6 +341,10 @@ void Context::finalize() {
         const size_t tiles = (size_t)tc_argmax_tiles(vocab_);
         amax_val_.alloc(M * tiles * 4);
         amax_idx_.alloc(M * tiles * 4);
+        if (vocab_rescore_) {
+            cand_meta_.alloc((M * 3 + 1) * 4);
+            cand_list_.alloc(M * kVocabCandCap * sizeof(int2));
+        }
     } else {
         h32_.alloc(M * kDllm * 4);
         ctx32_.alloc(M * kDllm * 4);
@@ -602,14 +616,50 @@ void Context::ctc_dev(const float* d_enc, int batch, int frames, int32_t* d_ids)
             launch_argmax_rows(logits_.as<float>(), rows, vocab_, vocab_, d_ids + r0, stream_);
         }
     } else {
-        // the logits never reach HBM: the GEMM epilogue keeps a running (max, argmax) per 256-column tile
-        const Act h = h_act(kDenc);
-        launch_split_planes(x, (int64_t)M * kDenc, h.pl, stream_);
-        Epilogue e;
-        e.amax_val = amax_val_.as<float>(); e.amax_idx = amax_idx_.as<int32_t>();
-        linear(h, ctc_lo_, M, e);
-        launch_argmax_combine(amax_val_.as<float>(), amax_idx_.as<int32_t>(), M, tc_argmax_tiles(vocab_), d_ids, stream_);
+        vocab_argmax(x, h_act(kDenc).pl, ctc_lo_, vocab_wnorm_, M, vocab_rescore_ ? cand_workspace() : VocabCand{},
+                     amax_val_.as<float>(), amax_idx_.as<int32_t>(), d_ids);
     }
+}
+
+VocabCand Context::cand_workspace() const {
+    VocabCand c;
+    c.run_max = cand_meta_.as<int32_t>();
+    c.count = c.run_max + m_max_;
+    c.bound2 = reinterpret_cast<const float*>(c.count + m_max_);
+    c.overflowed = c.count + 2 * m_max_;
+    c.list = cand_list_.as<int2>();
+    c.cap = kVocabCandCap;
+    return c;
+}
+
+// The logits never reach HBM.  With candidate lists (bf16x3 mode, batches of at least half a wave of 256-row blocks):
+// one bf16 product per element finds every column that can hold the row maximum and those few are rescored exactly
+// (kernels.h); rows with more than kVocabCandCap such columns take the gated second-chance pass.  Without: the
+// projection runs at the context's precision and the epilogue keeps a running (max, first index) per 128 columns.
+void Context::vocab_argmax(const float* x, Planes x_pl, const Linear& lo, float w_norm_max, int m, VocabCand cand,
+                           float* amax_val, int32_t* amax_idx, int32_t* d_ids) {
+    const int64_t plane_stride = x_pl.lo - x_pl.hi;
+    const TcOperand opa = tc_make_operand(x_pl.hi, m, lo.k, lo.k, plane_stride, 2, kTcBlockM);
+    Epilogue e;
+    e.bias = lo.b;
+    // a short batch would spread every row over many concurrent pairs, each starting its running maximum from
+    // nothing: long lists for flat logits and no time to win back, so it keeps the three-product projection
+    const bool use_cand = cand.list && 2 * cdiv(m, 2 * kTcBlockM) >= tc_num_pairs();
+    if (use_cand) {
+        launch_vocab_prepare(x, m, lo.k, w_norm_max, x_pl, cand, stream_);
+        e.cand = cand;
+        launch_gemm_tc(opa, lo.op, m, lo.n, lo.k, 1, e, stream_);
+        launch_vocab_rescore(x, lo.w, lo.b, m, lo.k, lo.n, cand, d_ids, stream_);
+        Epilogue e2;
+        e2.bias = lo.b; e2.amax_val = amax_val; e2.amax_idx = amax_idx; e2.gate = cand.overflowed;
+        launch_gemm_tc(opa, lo.op, m, lo.n, lo.k, 2, e2, stream_);
+        launch_argmax_combine(amax_val, amax_idx, m, tc_argmax_tiles(lo.n), d_ids, stream_, cand.count, cand.cap);
+        return;
+    }
+    launch_split_planes(x, (int64_t)m * lo.k, x_pl, stream_);
+    e.amax_val = amax_val; e.amax_idx = amax_idx;
+    launch_gemm_tc(opa, lo.op, m, lo.n, lo.k, prec_ == kBf16x3 ? 2 : 1, e, stream_);
+    launch_argmax_combine(amax_val, amax_idx, m, tc_argmax_tiles(lo.n), d_ids, stream_);
 }
 
 void Context::collapse_dev(const int32_t* d_ids, int batch, int frames, int32_t* d_tokens, int32_t* d_starts,
@@ -738,21 +788,58 @@ void Context::test_vocab_argmax(const float* a, const float* w, const float* bia
         launch_argmax_rows(dl.as<float>(), m, n, n, dids.as<int32_t>(), stream_);
         FA_CUDA(cudaStreamSynchronize(stream_));
     } else {
-        DevBuf dpl_a, dpl_w, dv, di;
+        DevBuf dpl_a, dpl_w, dv, di, dmeta, dlist, dnorm;
         const int tiles = tc_argmax_tiles(n);
         dpl_a.alloc((size_t)2 * m * k * 2); dpl_w.alloc((size_t)2 * n * k * 2);
         dv.alloc((size_t)m * tiles * 4); di.alloc((size_t)m * tiles * 4);
         Planes pa{dpl_a.as<__nv_bfloat16>(), dpl_a.as<__nv_bfloat16>() + (size_t)m * k};
         Planes pw{dpl_w.as<__nv_bfloat16>(), dpl_w.as<__nv_bfloat16>() + (size_t)n * k};
-        launch_split_planes(da.as<float>(), (int64_t)m * k, pa, stream_);
         launch_split_planes(dw.as<float>(), (int64_t)n * k, pw, stream_);
-        const TcOperand oa = tc_make_operand(pa.hi, m, k, k, (int64_t)m * k, 2, kTcBlockM);
-        const TcOperand ow = tc_make_weight(pw.hi, n, k, (int64_t)n * k, 2);
-        Epilogue e;
-        e.bias = db.as<float>(); e.amax_val = dv.as<float>(); e.amax_idx = di.as<int32_t>();
-        launch_gemm_tc(oa, ow, m, n, k, precision == kBf16x3 ? 2 : 1, e, stream_);
-        launch_argmax_combine(dv.as<float>(), di.as<int32_t>(), m, tiles, dids.as<int32_t>(), stream_);
+        Linear lo;
+        lo.w = dw.as<float>(); lo.b = db.as<float>(); lo.n = n; lo.k = k;
+        lo.op = tc_make_weight(pw.hi, n, k, (int64_t)n * k, 2);
+        VocabCand cand;
+        float wnorm = 0.f;
+        const char* vm = getenv("FUNASR_B200_VOCAB");
+        if (precision == kBf16x3 && !(vm && std::string(vm) == "full")) {
+            dmeta.alloc(((size_t)m * 3 + 1) * 4); dlist.alloc((size_t)m * kVocabCandCap * sizeof(int2)); dnorm.alloc(4);
+            cand.run_max = dmeta.as<int32_t>(); cand.count = cand.run_max + m;
+            cand.bound2 = reinterpret_cast<const float*>(cand.count + m);
+            cand.overflowed = cand.count + 2 * m;
+            cand.list = dlist.as<int2>(); cand.cap = kVocabCandCap;
+            launch_row_norm_max(lo.w, n, k, dnorm.as<float>(), stream_);
+            FA_CUDA(cudaMemcpyAsync(&wnorm, dnorm.p, 4, cudaMemcpyDeviceToHost, stream_));
+            FA_CUDA(cudaStreamSynchronize(stream_));
+        }
+        const int saved = prec_;
+        prec_ = precision;
+        try {
+            vocab_argmax(da.as<float>(), pa, lo, wnorm, m, cand, dv.as<float>(), di.as<int32_t>(), dids.as<int32_t>());
+        } catch (...) { prec_ = saved; throw; }
+        prec_ = saved;
         FA_CUDA(cudaStreamSynchronize(stream_));
+        if (cand.list && 2 * cdiv(m, 2 * kTcBlockM) >= tc_num_pairs() && getenv("FUNASR_B200_VOCAB_STATS")) {       // tuning aid: how long the lists get
+            std::vector<int32_t> meta((size_t)3 * m);
+            std::vector<int2> lst((size_t)m * kVocabCandCap);
+            FA_CUDA(cudaMemcpy(meta.data(), dmeta.p, meta.size() * 4, cudaMemcpyDeviceToHost));
+            FA_CUDA(cudaMemcpy(lst.data(), dlist.p, lst.size() * sizeof(int2), cudaMemcpyDeviceToHost));
+            double sum = 0, surv = 0;
+            int mx = 0, over = 0;
+            for (int r = 0; r < m; ++r) {
+                const int c = meta[(size_t)m + r];
+                sum += c; mx = std::max(mx, c); over += c > kVocabCandCap;
+                const int32_t o = meta[r];
+                const int32_t bits = o >= 0 ? o : o ^ 0x7fffffff;
+                float rm, b2;
+                memcpy(&rm, &bits, 4); memcpy(&b2, &meta[(size_t)2 * m + r], 4);
+                for (int i = 0; i < std::min(c, kVocabCandCap); ++i) {
+                    float v; memcpy(&v, &lst[(size_t)r * kVocabCandCap + i].y, 4);
+                    surv += v >= rm - b2;
+                }
+            }
+            fprintf(stderr, "vocab candidates: rows %d, listed mean %.1f max %d, overflowed rows %d, rescored mean %.2f\n", m,
+                    sum / m, mx, over, surv / m);
+        }
     }
     FA_CUDA(cudaMemcpy(ids, dids.p, dids.bytes, cudaMemcpyDeviceToHost));
 }

@@ -123,6 +123,10 @@ private:
     Act h_act(int ld) const;
     Act ctx_act(int ld) const;
     Act ffn_act(int ld) const;
+    // a14 on the tensor cores: argmax over the vocabulary of x[M][k] * W^T + b without the logits reaching HBM
+    void vocab_argmax(const float* x, Planes x_pl, const Linear& lo, float w_norm_max, int m, VocabCand cand,
+                      float* amax_val, int32_t* amax_idx, int32_t* d_ids);
+    VocabCand cand_workspace() const;
 
     int device_, max_batch_, prec_, vocab_ = 0;
     int64_t max_samples_;
@@ -147,7 +151,9 @@ private:
 
     // workspace
     DevBuf audio_, partials_, logmel_, x0_, x_, h32_, hpl_, qkv_, qkvpl_, ctx32_, ctxpl_, ffn32_, ffnpl_, encpl_, enc_,
-        adaptor_out_, ids_, amax_val_, amax_idx_, logits_, lens_, tokens_;
+        adaptor_out_, ids_, amax_val_, amax_idx_, logits_, lens_, tokens_, cand_meta_, cand_list_;
+    float vocab_wnorm_ = 0.f;                 // max_c |w_c|_2 of ctc_lo (bound of the one-product vocabulary pass)
+    bool vocab_rescore_ = false;              // bf16x3: one-product pass + exact rescoring of the candidates
     int* d_nvalid_ = nullptr;
     int* d_tvalid_ = nullptr;
     int* d_tlen_ = nullptr;

@@ -73,6 +73,12 @@ struct EpiParams {
     __nv_bfloat16* out_lo;
     float* amax_val;
     int32_t* amax_idx;
+    int32_t* cand_run_max;                       // vocabulary candidate lists (kernels.h: VocabCand)
+    int32_t* cand_count;
+    int2* cand_list;
+    const float* cand_bound2;
+    int cand_cap;
+    const int32_t* gate;                         // launch does nothing when *gate == 0
     int ldr, ldc, ldp, relu, n_slots;            // n_slots: 128-column groups of N (fused argmax partials)
     float pl_col_scale;
     int pl_col_scale_end, f32_col_begin;
@@ -96,6 +102,13 @@ __device__ __forceinline__ void tile_coords(int tile, int m_tiles, int n_tiles, 
     nt = r / rows;
     mt = b * band + (r - nt * rows);
 }
+
+// order-preserving int encoding of a float (atomicMax on signed ints); same as rowops.cu
+__device__ __forceinline__ int32_t f2ord_dev(float f) {
+    const int32_t b = __float_as_int(f);
+    return b >= 0 ? b : b ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ord2f_dev(int32_t o) { return __int_as_float(o >= 0 ? o : o ^ 0x7fffffff); }
 
 // Epilogue of one output unit: rows row0..row0+127 (this CTA's TMEM lanes), columns n0..n0+nw-1 held
 // in TMEM columns tmem_acc..tmem_acc+nw-1.  Run by the 8 epilogue warps of a CTA.
@@ -172,6 +185,29 @@ __device__ __forceinline__ void epilogue_unit(const EpiParams& ep, const CUtenso
                 if (col0 + j < n && v[j] > best) { best = v[j]; best_i = col0 + j; }
             continue;
         }
+        if (ep.cand_list) {
+            // `best` is this warp's running maximum of the row, seeded from the row's global running maximum (possibly
+            // stale, hence lower: the test below is then looser, never tighter).  Every column within bound2 of it
+            // can still be the true argmax and is appended with its approximate logit, so that the rescoring kernel
+            // can drop the entries the final maximum rules out.
+            if (cc == 0 && row < m) best = ord2f_dev(__ldcg(ep.cand_run_max + row));     // L2: other SMs raise it
+            float cm = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (col0 + j < n) cm = fmaxf(cm, v[j]);
+            best = fmaxf(best, cm);
+            if (row < m) {
+                const float thr = best - ep.cand_bound2[row];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (col0 + j < n && v[j] >= thr) {
+                        const int pos = atomicAdd(ep.cand_count + row, 1);
+                        if (pos < ep.cand_cap) ep.cand_list[(int64_t)row * ep.cand_cap + pos] = make_int2(col0 + j, __float_as_int(v[j]));
+                    }
+                }
+            }
+            continue;
+        }
         if (ep.relu) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
@@ -240,9 +276,12 @@ __device__ __forceinline__ void epilogue_unit(const EpiParams& ep, const CUtenso
 #pragma unroll
         for (int i = 0; i < 8; ++i) rv[i] = rv_next[i];
     }
-    if (ep.amax_val && any) {
+    if (ep.cand_list && any && row < m) atomicMax(ep.cand_run_max + row, f2ord_dev(best));
+    if (ep.amax_val && half * 128 < nw) {
         // one partial slot per (row, 128-column group): the two column halves of a 256-wide tile live in
-        // different warps, and a half tile of the tail is exactly one group
+        // different warps, and a half tile of the tail is exactly one group.  A group that lies wholly past N
+        // (the last tile of the vocabulary) still gets its slot written — (-inf, none) — because the combine
+        // kernel reads every slot.
         if (row < m) {
             const int slot = (n0 >> 7) + half;
             ep.amax_val[(int64_t)row * ep.n_slots + slot] = best;
@@ -269,7 +308,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
 
     const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
-    const int m_tiles = (m + BM - 1) / BM, n_tiles = (n + BN - 1) / BN, num_tiles = m_tiles * n_tiles;
+    const int m_tiles = (m + BM - 1) / BM, n_tiles = (n + BN - 1) / BN;
+    int num_tiles = m_tiles * n_tiles;
     const int k_blocks = (k + BK - 1) / BK;
 
     if (threadIdx.x == 0) {
@@ -296,6 +336,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_ptr, 0);    // provably warp-uniform
     grid_dependency_wait();                       // everything above overlapped the previous kernel's tail
+    if (ep.gate && __ldcg(ep.gate) == 0) num_tiles = 0;                   // gated launch with nothing to do
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
@@ -488,6 +529,7 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_ptr, 0);    // provably warp-uniform
     grid_dependency_wait();                       // everything above overlapped the previous kernel's tail
+    if (ep.gate && __ldcg(ep.gate) == 0) sched.total_units = 0;           // gated launch with nothing to do
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer (both CTAs)
@@ -596,6 +638,258 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
     }
 }
 
+// ------------------------------------------------------------------------------------ A-resident pair kernel
+// The vocabulary projection in its one-product form (NP = 1, K <= 512, candidate-list epilogue, nothing stored) is
+// bound by the L2 -> SM feed in k_gemm_tc2: 32 KB per K-block per SM against 512 tensor cycles is 64 B/clk/SM,
+// above what the L2 delivers to all SMs at once.  Here a pair keeps its 256 x K block of A in shared memory
+// (128 KB per CTA) and walks a run of consecutive 256-column tiles of W, so only W streams: 16 KB per K-block per
+// SM.  Work items are (256-row block, run of n-tiles); consecutive items are different row blocks of the same
+// run, so the pairs running together read the same W tiles (L2) and a row is almost never in two pairs at once,
+// which keeps the running maxima of the candidate lists tight.  With a K this short the epilogue (one pass over
+// 256 x 256 approximate logits per 4096 tensor cycles) is the other limiter: 16 epilogue warps per CTA, two
+// 32-column chunks each, TMEM loads one chunk ahead, the tile's bias staged in shared memory before the
+// accumulator is ready, and the append path entered only by lanes whose chunk maximum passes the row's test.
+struct SchedAR {
+    int m_tiles, n_tiles, groups, group_tiles, items;
+};
+struct CfgAR {
+    static constexpr int kMaxKBlocks = 8;
+    static constexpr int kABytes = kMaxKBlocks * kATileBytes;                 // 128 KB
+    static constexpr int kHalfWBytes = (BN / 2) * BK * 2;                     // 16 KB
+    static constexpr int kStages = 5;
+    static constexpr int kEpiWarps = 16, kChunks = 2;                         // 16 warps x 2 chunks x 32 columns = 4 quarters x 256
+    static constexpr int kThreads = 64 + 32 * kEpiWarps;
+    static constexpr int kBiasBytes = kEpiWarps * kChunks * 32 * 4;           // 4 KB
+    static constexpr int kSmemBytes = kABytes + kStages * kHalfWBytes + kBiasBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// One 32-column chunk of approximate logits (already biased): raise the running maximum, append what passes.
+__device__ __forceinline__ void cand_chunk(const EpiParams& ep, const float (&v)[32], int col0, int n, int row, bool row_live,
+                                           float bound2, float& best) {
+    float cm = -INFINITY;
+    if (col0 + 32 <= n) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) cm = fmaxf(cm, v[j]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (col0 + j < n) cm = fmaxf(cm, v[j]);
+    }
+    best = fmaxf(best, cm);
+    const float thr = best - bound2;
+    if (row_live && cm >= thr) {                 // rare per lane: this chunk holds a column within bound2 of the maximum so far
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            if (col0 + j < n && v[j] >= thr) {
+                int pos;
+                asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(pos) : "l"(ep.cand_count + row) : "memory");
+                if (pos < ep.cand_cap) ep.cand_list[(int64_t)row * ep.cand_cap + pos] = make_int2(col0 + j, __float_as_int(v[j]));
+            }
+        }
+    }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CfgAR::kThreads, 1)
+k_gemm_tc2_ar(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, int m, int n, int k,
+              SchedAR sched, EpiParams ep) {
+    using C = CfgAR;
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t a_base = (raw + 1023u) & ~1023u;
+    const uint32_t w_base = a_base + C::kABytes;
+    const uint32_t bias_base = w_base + C::kStages * C::kHalfWBytes;
+    const uint32_t bars = bias_base + C::kBiasBytes;
+    const uint32_t bar_full = bars, bar_empty = bars + 8 * C::kStages;
+    const uint32_t bar_tfull = bars + 16 * C::kStages, bar_tempty = bar_tfull + 16;
+    const uint32_t bar_afull = bar_tempty + 16, bar_aempty = bar_afull + 8;
+    const uint32_t tmem_slot = bar_aempty + 8;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+    const int rank = (int)cluster_ctarank();
+    const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+    const int k_blocks = (k + BK - 1) / BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C::kStages; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(bar_tfull + 8 * a, 1);
+            mbar_init(bar_tempty + 8 * a, 2 * C::kEpiWarps);
+        }
+        mbar_init(bar_afull, 1);                  // leader only: one arrive.expect_tx for both CTAs' A blocks
+        mbar_init(bar_aempty, 1);                 // multicast commit after the last MMA of an item, in each CTA
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_ptr, 0);
+    grid_dependency_wait();
+
+    auto item_coords = [&](int item, int& mt, int& nt0, int& nt1) {
+        const int g = item / sched.m_tiles;
+        mt = item - g * sched.m_tiles;
+        nt0 = g * sched.group_tiles;
+        nt1 = min(sched.n_tiles, nt0 + sched.group_tiles);
+    };
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer (both CTAs)
+        int stage = 0;
+        uint32_t phase = 0, a_phase = 0;
+        for (int item = pair; item < sched.items; item += num_pairs, a_phase ^= 1) {
+            int mt, nt0, nt1;
+            item_coords(item, mt, nt0, nt1);
+            const int a_row = (mt * 2 + rank) * BM;
+            mbar_wait(bar_aempty, a_phase ^ 1);                       // the previous item's MMAs have read A
+            if (elect_one()) {
+                if (rank == 0) mbar_arrive_expect_tx(bar_afull, 2u * (uint32_t)k_blocks * kATileBytes);
+                const uint32_t afull = leader_addr(bar_afull);
+                for (int kb = 0; kb < k_blocks; ++kb)
+                    tma_load_3d_pair(a_base + kb * kATileBytes, &map_a, afull, kb * BK, a_row, 0);
+            }
+            __syncwarp();
+            for (int nt = nt0; nt < nt1; ++nt) {
+                const int w_row = nt * BN + rank * (BN / 2);
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    const uint32_t wdst = w_base + stage * C::kHalfWBytes;
+                    const uint32_t full = leader_addr(bar_full + 8 * stage);
+                    if (elect_one()) {
+                        if (rank == 0) mbar_arrive_expect_tx(bar_full + 8 * stage, 2u * C::kHalfWBytes);
+                        tma_load_3d_pair(wdst, &map_w, full, kb * BK, w_row, 0);
+                        tma_load_3d_pair(wdst + 64 * BK * 2, &map_w, full, kb * BK, w_row + 64, 0);
+                    }
+                    __syncwarp();
+                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+        if (rank == 0) {
+            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0, a_phase = 0;
+            int it = 0;
+            for (int item = pair; item < sched.items; item += num_pairs, a_phase ^= 1) {
+                int mt, nt0, nt1;
+                item_coords(item, mt, nt0, nt1);
+                mbar_wait(bar_afull, a_phase);
+                for (int nt = nt0; nt < nt1; ++nt, ++it) {
+                    const int acc = it & 1;
+                    const uint32_t acc_phase = (it >> 1) & 1;
+                    mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+                    tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + acc * BN;
+                    for (int kb = 0; kb < k_blocks; ++kb) {
+                        mbar_wait(bar_full + 8 * stage, phase);
+                        tc_fence_after();
+                        const uint32_t a_t = a_base + kb * kATileBytes, w_t = w_base + stage * C::kHalfWBytes;
+                        if (elect_one()) {
+#pragma unroll
+                            for (int ks = 0; ks < BK / 16; ++ks)
+                                tc_mma_pair(tmem_d, umma_desc_sw128(a_t + ks * 32), umma_desc_sw128(w_t + ks * 32), idesc,
+                                            (kb | ks) ? 1u : 0u);
+                            tc_commit_pair(bar_empty + 8 * stage);
+                            if (kb == k_blocks - 1) {
+                                tc_commit_pair(bar_tfull + 8 * acc);
+                                if (nt == nt1 - 1) tc_commit_pair(bar_aempty);        // A may be overwritten
+                            }
+                        }
+                        __syncwarp();
+                        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------------------------------------------ epilogue (16 warps in each CTA)
+        const int e = warp - 2;
+        const int quarter = (e + 2) & 3, c_first = (e >> 2) * C::kChunks;    // TMEM lane quarter = warp id % 4
+        float* wbias = reinterpret_cast<float*>(smem_raw + (bias_base - raw)) + e * (C::kChunks * 32);
+        int it = 0;
+        for (int item = pair; item < sched.items; item += num_pairs) {
+            int mt, nt0, nt1;
+            item_coords(item, mt, nt0, nt1);
+            const int row = (mt * 2 + rank) * BM + quarter * 32 + lane;
+            const bool row_live = row < m;
+            // the row's running maximum lives in a register for the whole run of tiles; other pairs (other runs of the
+            // same rows) may have raised the global one meanwhile: a stale value only lengthens the list
+            float best = row_live ? ord2f_dev(__ldcg(ep.cand_run_max + row)) : -INFINITY;
+            const float bound2 = row_live ? ep.cand_bound2[row] : 0.f;
+            const uint32_t taddr_row = ((uint32_t)(quarter * 32) << 16) + c_first * 32;
+            for (int nt = nt0; nt < nt1; ++nt, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                const int col_w = nt * BN + c_first * 32;                    // this warp's 64 columns
+                // bias of those columns into the warp's shared slice while the accumulator is still being computed
+                __syncwarp();
+                {
+                    const int c = col_w + 2 * lane;
+                    float2 b2v;
+                    b2v.x = c < n ? __ldg(ep.bias + c) : 0.f;
+                    b2v.y = c + 1 < n ? __ldg(ep.bias + c + 1) : 0.f;
+                    *reinterpret_cast<float2*>(wbias + 2 * lane) = b2v;
+                }
+                __syncwarp();
+                mbar_wait(bar_tfull + 8 * acc, acc_phase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + acc * BN + taddr_row;
+                uint32_t r0[32], r1[32];
+                tc_ld32(taddr, r0);
+                tc_wait_ld();
+                tc_ld32(taddr + 32, r1);                                     // in flight while chunk 0 is examined
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(wbias + 4 * j);
+                    v[4 * j] = __fadd_rn(__uint_as_float(r0[4 * j]), b4.x);
+                    v[4 * j + 1] = __fadd_rn(__uint_as_float(r0[4 * j + 1]), b4.y);
+                    v[4 * j + 2] = __fadd_rn(__uint_as_float(r0[4 * j + 2]), b4.z);
+                    v[4 * j + 3] = __fadd_rn(__uint_as_float(r0[4 * j + 3]), b4.w);
+                }
+                if (col_w < n) cand_chunk(ep, v, col_w, n, row, row_live, bound2, best);
+                tc_wait_ld();
+                // the accumulator has been read: hand it back before the second chunk is examined
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(leader_addr(bar_tempty + 8 * acc));
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(wbias + 32 + 4 * j);
+                    v[4 * j] = __fadd_rn(__uint_as_float(r1[4 * j]), b4.x);
+                    v[4 * j + 1] = __fadd_rn(__uint_as_float(r1[4 * j + 1]), b4.y);
+                    v[4 * j + 2] = __fadd_rn(__uint_as_float(r1[4 * j + 2]), b4.z);
+                    v[4 * j + 3] = __fadd_rn(__uint_as_float(r1[4 * j + 3]), b4.w);
+                }
+                if (col_w + 32 < n) cand_chunk(ep, v, col_w + 32, n, row, row_live, bound2, best);
+            }
+            if (row_live) atomicMax(ep.cand_run_max + row, f2ord_dev(best));
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------------------------ host side
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -619,6 +913,7 @@ void tc_init_device() {
     FA_CUDA(cudaFuncSetAttribute(k_gemm_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::kSmemBytes));
     FA_CUDA(cudaFuncSetAttribute(k_gemm_tc2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<1>::kSmemBytes));
     FA_CUDA(cudaFuncSetAttribute(k_gemm_tc2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<2>::kSmemBytes));
+    FA_CUDA(cudaFuncSetAttribute(k_gemm_tc2_ar, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgAR::kSmemBytes));
     int dev = 0;
     FA_CUDA(cudaGetDevice(&dev));
     FA_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -677,6 +972,7 @@ TcOperand tc_make_weight(const __nv_bfloat16* base, int rows, int k, int64_t pla
     return op;
 }
 
+int tc_num_pairs() { return g_num_pairs; }
 int tc_argmax_tiles(int n) { return 2 * cdiv(n, BN); }   // one partial slot per 128 columns
 
 namespace {
@@ -689,6 +985,10 @@ int gemm_kernel_override() {
     if (!strcmp(s, "2cta")) return 2;
     return 0;
 }
+bool gemm_ar_enabled() {
+    const char* s = getenv("FUNASR_B200_GEMM_AR");
+    return !(s && s[0] == '0');
+}
 }  // namespace
 
 void launch_gemm_tc(const TcOperand& a, const TcOperand& w, int m, int n, int k, int n_planes, const Epilogue& e,
@@ -699,6 +999,8 @@ void launch_gemm_tc(const TcOperand& a, const TcOperand& w, int m, int n, int k,
     EpiParams ep{};
     ep.bias = e.bias; ep.resid = e.resid; ep.out = e.out_f32; ep.out_hi = e.out_pl.hi; ep.out_lo = e.out_pl.lo;
     ep.amax_val = e.amax_val; ep.amax_idx = e.amax_idx;
+    ep.cand_run_max = e.cand.run_max; ep.cand_count = e.cand.count; ep.cand_list = e.cand.list; ep.cand_bound2 = e.cand.bound2;
+    ep.cand_cap = e.cand.cap; ep.gate = e.gate;
     ep.ldr = e.ldr; ep.ldc = e.ldc; ep.ldp = e.ldp; ep.relu = e.relu ? 1 : 0; ep.n_slots = tc_argmax_tiles(n);
     ep.pl_col_scale = e.pl_col_scale; ep.pl_col_scale_end = e.pl_col_scale_end; ep.f32_col_begin = e.f32_col_begin;
     FA_REQUIRE(e.pl_col_scale_end % 32 == 0 && e.f32_col_begin % 32 == 0, "column ranges of the epilogue must be multiples of 32");
@@ -729,6 +1031,26 @@ void launch_gemm_tc(const TcOperand& a, const TcOperand& w, int m, int n, int k,
     // tiles of the single-CTA kernel spread a small M over twice as many SMs.
     const int pair_tiles = cdiv(m, 2 * BM) * cdiv(n, BN);
     const int force = gemm_kernel_override();
+    // one-product projections that store nothing (the vocabulary argmax epilogues) and whose K fits: A stays in
+    // shared memory, only W streams.  FUNASR_B200_GEMM_AR=0 falls back to the general pair kernel (comparison aid).
+    const bool no_stores = !ep.out && !ep.out_hi && !ep.resid && ep.cand_list;
+    if (w.has64 && force != 1 && n_planes == 1 && no_stores && cdiv(k, BK) <= CfgAR::kMaxKBlocks &&
+        pair_tiles >= 2 * g_num_pairs && gemm_ar_enabled()) {
+        SchedAR s{};
+        s.m_tiles = cdiv(m, 2 * BM); s.n_tiles = cdiv(n, BN);
+        // runs of n-tiles: as few (long) as keep the last round of items full; an item also pays ~1.5 tile times for its A block
+        double best_cost = 0.0;
+        for (int g = 1; g <= 32 && g <= s.n_tiles; ++g) {
+            const int gt = cdiv(s.n_tiles, g), items = s.m_tiles * cdiv(s.n_tiles, gt);
+            const double cost = (double)cdiv(items, g_num_pairs) * (gt + 1.5);
+            if (g == 1 || cost < best_cost) { best_cost = cost; s.group_tiles = gt; }
+        }
+        s.groups = cdiv(s.n_tiles, s.group_tiles);
+        s.items = s.m_tiles * s.groups;
+        const int pairs = s.items < g_num_pairs ? s.items : g_num_pairs;
+        FA_LAUNCH(k_gemm_tc2_ar, 2 * pairs, CfgAR::kThreads, CfgAR::kSmemBytes, st, a.map, w.map64, m, n, k, s, ep);
+        return;
+    }
     if (w.has64 && force != 1 && (force == 2 || pair_tiles >= g_num_pairs)) {
         Sched s{};
         s.m_tiles = cdiv(m, 2 * BM); s.n_tiles = cdiv(n, BN); s.band = 8;

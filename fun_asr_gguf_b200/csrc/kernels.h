@@ -45,12 +45,24 @@ void launch_split_planes(const float* x, int64_t n, Planes out, cudaStream_t st)
 // ids[r] = first argmax over logits[r][0..n)
 void launch_argmax_rows(const float* logits, int rows, int n, int ld, int32_t* ids, cudaStream_t st);
 // combine per-tile (max, idx) partials written by the fused vocabulary GEMM epilogue
-void launch_argmax_combine(const float* pmax, const int32_t* pidx, int rows, int tiles, int32_t* ids, cudaStream_t st);
+// only_if_over: write only the rows whose only_if_over[row] > over (second-chance pass of the candidate path)
+void launch_argmax_combine(const float* pmax, const int32_t* pidx, int rows, int tiles, int32_t* ids, cudaStream_t st,
+                           const int32_t* only_if_over = nullptr, int over = 0);
 // greedy collapse: ids [B][T] -> per segment (token, start_frame) pairs, blanks dropped (nano_ctc.py:70-99)
 void launch_ctc_collapse(const int32_t* ids, int batch, int frames, int blank, int32_t* tokens, int32_t* starts,
                          int32_t* counts, cudaStream_t st);
 
 // ---------------------------------------------------------------- dense projections (§8a a6, a9, a11, a13, a14)
+// Candidate lists of the vocabulary argmax (see launch_vocab_prepare / launch_vocab_rescore).
+constexpr int kVocabCandCap = 192;   // list slots per row; a row that needs more is rescored over the whole vocabulary
+struct VocabCand {
+    int32_t* run_max = nullptr;      // [M] running approximate row maximum, order-preserving int encoding of the float
+    int32_t* count = nullptr;        // [M] candidates appended so far (may exceed cap: the row then takes the second-chance pass)
+    int32_t* overflowed = nullptr;   // [1] rows whose list overflowed; gates the second-chance pass
+    int2* list = nullptr;            // [M][cap] (column, bits of its approximate logit), in no particular order
+    const float* bound2 = nullptr;   // [M] twice the worst-case error of a one-product logit of that row
+    int cap = 0;
+};
 struct Epilogue {
     const float* bias = nullptr;     // [N]
     const float* resid = nullptr;    // [M][ldr] added after bias
@@ -66,6 +78,11 @@ struct Epilogue {
     // fused vocabulary argmax: per (row, n-tile) partial max/idx instead of the logits
     float* amax_val = nullptr;       // [M][n_tiles]
     int32_t* amax_idx = nullptr;
+    // vocabulary candidates (one-product pass): instead of logits or partial maxima, every column whose approximate
+    // logit is within bound2[row] of the running approximate row maximum is appended to the row's list
+    VocabCand cand;
+    // the whole launch is a no-op when *gate == 0 (read on the device: no host round trip)
+    const int32_t* gate = nullptr;
 };
 // C = A[M][K] * W[N][K]^T  in fp32 on the CUDA cores (exact-precision mode and on-device arbiter).
 void launch_gemm_simt(const float* a, int lda, const float* w, int m, int n, int k, const Epilogue& ep, cudaStream_t st);
@@ -85,6 +102,22 @@ constexpr int kTcBlockM = 128, kTcBlockN = 256, kTcBlockK = 64;
 void launch_gemm_tc(const TcOperand& a, const TcOperand& w, int m, int n, int k, int n_planes, const Epilogue& ep,
                     cudaStream_t st);
 int tc_argmax_tiles(int n);
+int tc_num_pairs();      // CTA pairs of the tcgen05 GEMM that run at once (74 on a full B200)
+
+// Vocabulary argmax in two steps (CTC.ctc_lo + torch.argmax, model_definition.py:216-221,337):
+//   1. the projection runs with ONE bf16 product per element; its worst-case error against the fp32 logit is
+//      b_r = 2^-8 * 1.05 * |x_r|_2 * max_c |w_c|_2, so every column that can hold the true maximum has an approximate
+//      logit within 2 b_r of the approximate maximum and lands in the row's candidate list;
+//   2. the candidates (a handful per row) are rescored with an fp32 dot product and the first maximal index wins.
+// prepare: planes of x, |x_r|, bound2, list reset.  rescore: ids of the rows whose list did not overflow.  The rest
+// (none, unless a row has more than kVocabCandCap near-maximal columns) take the second-chance pass: the
+// three-product projection with the fused running argmax, launched behind a device-side gate so that it costs a few
+// microseconds when no row needs it.
+void launch_vocab_prepare(const float* x, int rows, int d, float w_norm_max, Planes x_pl, VocabCand c, cudaStream_t st);
+void launch_vocab_rescore(const float* x, const float* w, const float* bias, int rows, int d, int n, VocabCand c, int32_t* ids,
+                          cudaStream_t st);
+// max over rows of |w_row|_2, left in *out (device)
+void launch_row_norm_max(const float* w, int rows, int d, float* out, cudaStream_t st);
 
 // ---------------------------------------------------------------- attention (§8a a8)
 // q,k,v: fp32 [B*T][ld], head h at column offset h*dk of each pointer.  kv_len[b] keys are attended

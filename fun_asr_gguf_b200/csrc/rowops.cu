@@ -200,11 +200,12 @@ k_argmax_rows(const float* __restrict__ logits, int n, int ld, int32_t* __restri
 
 __global__ void __launch_bounds__(256)
 k_argmax_combine(const float* __restrict__ pmax, const int32_t* __restrict__ pidx, int rows, int tiles,
-                 int32_t* __restrict__ ids) {
+                 int32_t* __restrict__ ids, const int32_t* __restrict__ only_if_over, int over) {
     grid_dependency_wait();
     // one warp per row: lanes stride over the tiles, then merge (value desc, index asc)
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= rows) return;
+    if (only_if_over && only_if_over[row] <= over) return;      // second-chance pass of the candidate path: overflowed rows only
     float bv = -INFINITY;
     int bi = 0x7fffffff;
     for (int t = lane; t < tiles; t += 32) amax_merge(bv, bi, pmax[(int64_t)row * tiles + t], pidx[(int64_t)row * tiles + t]);
@@ -212,6 +213,103 @@ k_argmax_combine(const float* __restrict__ pmax, const int32_t* __restrict__ pid
         const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
         const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
         amax_merge(bv, bi, ov, oi);
+    }
+    if (lane == 0) ids[row] = bi;
+}
+
+// ------------------------------------------------------------------------------------ vocabulary candidates
+// order-preserving int encoding of a float (for atomicMax on signed ints)
+__device__ __forceinline__ int32_t f2ord(float f) {
+    const int32_t b = __float_as_int(f);
+    return b >= 0 ? b : b ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ord2f(int32_t o) { return __int_as_float(o >= 0 ? o : o ^ 0x7fffffff); }
+
+__global__ void __launch_bounds__(256)
+k_row_norm_max(const float* __restrict__ w, int rows, int d, float* out) {
+    grid_dependency_wait();
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    float s = 0.f;
+    for (int i = lane; i < d; i += 32) { const float v = w[(int64_t)row * d + i]; s = fmaf(v, v, s); }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(sqrtf(s) * 1.000001f));   // non-negative floats order like ints
+}
+
+__global__ void __launch_bounds__(256)
+k_vocab_prepare(const float* __restrict__ x, int rows, int d, float w_norm_max, __nv_bfloat16* __restrict__ x_hi,
+                __nv_bfloat16* __restrict__ x_lo, int32_t* __restrict__ run_max, int32_t* __restrict__ count,
+                float* __restrict__ bound2, int32_t* __restrict__ overflowed) {
+    grid_dependency_wait();
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    float s = 0.f;
+    for (int i = lane * 4; i < d; i += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(x + (int64_t)row * d + i);
+        s = fmaf(v.x, v.x, s); s = fmaf(v.y, v.y, s); s = fmaf(v.z, v.z, s); s = fmaf(v.w, v.w, s);
+        uint2 h, l;
+        split_bf16x2(v.x, v.y, h.x, l.x);
+        split_bf16x2(v.z, v.w, h.y, l.y);
+        *reinterpret_cast<uint2*>(x_hi + (int64_t)row * d + i) = h;
+        *reinterpret_cast<uint2*>(x_lo + (int64_t)row * d + i) = l;      // only the second-chance pass reads it
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+        // |L - L~| <= 2^-8 (1 + 2^-10) sum |x_i||w_i| + accumulation rounding (K * 2^-22 of the same sum at worst)
+        // <= 2^-8 * 1.05 * |x| |w|; the list test uses twice that
+        bound2[row] = 2.0f * 0.00390625f * 1.05f * sqrtf(s) * w_norm_max;
+        run_max[row] = f2ord(-INFINITY);
+        count[row] = 0;
+        if (row == 0) *overflowed = 0;
+    }
+}
+
+// One warp per row.  The list holds every column that was within bound2 of the running maximum when its tile was
+// finished; only those within bound2 of the FINAL approximate maximum can hold the true maximum, and only they are
+// rescored: an fp32 dot product in a fixed lane / shuffle order, so the result does not depend on the
+// (non-deterministic) order of the list; ties go to the lowest index like torch.argmax.  A row whose list
+// overflowed is left to the second-chance pass (it is counted in *overflowed, which gates that pass).
+__global__ void __launch_bounds__(256)
+k_vocab_rescore(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, int rows, int d,
+                int n, const int32_t* __restrict__ run_max, const int32_t* __restrict__ count, const float* __restrict__ bound2,
+                const int2* __restrict__ list, int cap, int32_t* __restrict__ ids, int32_t* __restrict__ overflowed) {
+    grid_dependency_wait();
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* xr = x + (int64_t)row * d;
+    const int cnt = count[row];
+    if (cnt > cap) {
+        if (lane == 0) atomicAdd(overflowed, 1);
+        return;
+    }
+    const float thr = ord2f(run_max[row]) - bound2[row];
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    auto score = [&](int col) {
+        const float* wr = w + (int64_t)col * d;
+        float s = 0.f;
+        for (int i = lane * 4; i < d; i += 128) {
+            const float4 a = *reinterpret_cast<const float4*>(xr + i);
+            const float4 b = __ldg(reinterpret_cast<const float4*>(wr + i));
+            s = fmaf(a.x, b.x, s); s = fmaf(a.y, b.y, s); s = fmaf(a.z, b.z, s); s = fmaf(a.w, b.w, s);
+        }
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        s = __fadd_rn(s, bias[col]);
+        amax_merge(bv, bi, s, col);
+    };
+    for (int c0 = 0; c0 < cnt; c0 += 32) {
+        int2 e = make_int2(0, 0);
+        bool keep = false;
+        if (c0 + lane < cnt) {
+            e = list[(int64_t)row * cap + c0 + lane];
+            keep = __int_as_float(e.y) >= thr;
+        }
+        unsigned live = __ballot_sync(0xffffffffu, keep);
+        while (live) {
+            const int src = __ffs(live) - 1;
+            live &= live - 1;
+            score(__shfl_sync(0xffffffffu, e.x, src));
+        }
     }
     if (lane == 0) ids[row] = bi;
 }
@@ -293,8 +391,27 @@ void launch_argmax_rows(const float* logits, int rows, int n, int ld, int32_t* i
     FA_LAUNCH(k_argmax_rows, rows, 256, 0, st, logits, n, ld, ids);
 }
 
-void launch_argmax_combine(const float* pmax, const int32_t* pidx, int rows, int tiles, int32_t* ids, cudaStream_t st) {
-    FA_LAUNCH(k_argmax_combine, cdiv(rows, 8), 256, 0, st, pmax, pidx, rows, tiles, ids);
+void launch_argmax_combine(const float* pmax, const int32_t* pidx, int rows, int tiles, int32_t* ids, cudaStream_t st,
+                           const int32_t* only_if_over, int over) {
+    FA_LAUNCH(k_argmax_combine, cdiv(rows, 8), 256, 0, st, pmax, pidx, rows, tiles, ids, only_if_over, over);
+}
+
+void launch_row_norm_max(const float* w, int rows, int d, float* out, cudaStream_t st) {
+    FA_CUDA(cudaMemsetAsync(out, 0, sizeof(float), st));
+    FA_LAUNCH(k_row_norm_max, cdiv(rows, 8), 256, 0, st, w, rows, d, out);
+}
+
+void launch_vocab_prepare(const float* x, int rows, int d, float w_norm_max, Planes x_pl, VocabCand c, cudaStream_t st) {
+    FA_REQUIRE(d % 4 == 0, "vocab_prepare needs a width that is a multiple of 4");
+    FA_LAUNCH(k_vocab_prepare, cdiv(rows, 8), 256, 0, st, x, rows, d, w_norm_max, x_pl.hi, x_pl.lo, c.run_max, c.count,
+              const_cast<float*>(c.bound2), c.overflowed);
+}
+
+void launch_vocab_rescore(const float* x, const float* w, const float* bias, int rows, int d, int n, VocabCand c, int32_t* ids,
+                          cudaStream_t st) {
+    FA_REQUIRE(d % 4 == 0, "vocab_rescore needs a width that is a multiple of 4");
+    FA_LAUNCH(k_vocab_rescore, cdiv(rows, 8), 256, 0, st, x, w, bias, rows, d, n, c.run_max, c.count, c.bound2, c.list, c.cap, ids,
+              c.overflowed);
 }
 
 void launch_ctc_collapse(const int32_t* ids, int batch, int frames, int blank, int32_t* tokens, int32_t* starts,

@@ -71,7 +71,18 @@ def test_linear_pair_kernel_full_waves_and_split_tail(raw, monkeypatch, m, n, k)
     assert np.abs(planes - got).max() <= 2.0 ** -15 * np.abs(got).max()
 
 
-def test_vocab_argmax_pair_kernel_split_tail(raw, monkeypatch):
+@pytest.fixture(params=["rescore", "full"])
+def vocab_mode(request, monkeypatch):
+    """bf16x3 vocabulary argmax: one-product pass + exact rescoring of the candidate columns (default), or the
+    three-product projection with the fused running argmax (FUNASR_B200_VOCAB=full)."""
+    if request.param == "full":
+        monkeypatch.setenv("FUNASR_B200_VOCAB", "full")
+    else:
+        monkeypatch.delenv("FUNASR_B200_VOCAB", raising=False)
+    return request.param
+
+
+def test_vocab_argmax_pair_kernel_split_tail(raw, monkeypatch, vocab_mode):
     monkeypatch.delenv("FUNASR_B200_GEMM", raising=False)
     m, n = 2000, 5037                      # 8 x 20 pair tiles: two full waves of 74 and 12 tiles cut in halves
     a, w, bias = _rand((m, 512), 35), _rand((n, 512), 36, 512 ** -0.5), _rand((n,), 37, 0.1)
@@ -91,8 +102,8 @@ def test_bf16x3_is_much_closer_than_bf16(raw):
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
 @pytest.mark.parametrize("m,n", [(200, 5037), (131, 60515)])
-def test_vocab_argmax_never_materialises_logits(raw, gemm_kernel, precision, m, n):
-    if precision == "fp32" and gemm_kernel == "2cta":
+def test_vocab_argmax_never_materialises_logits(raw, gemm_kernel, vocab_mode, precision, m, n):
+    if precision == "fp32" and (gemm_kernel == "2cta" or vocab_mode == "full"):
         pytest.skip("fp32 mode does not use the tensor-core kernels")
     a, w, bias = _rand((m, 512), 8), _rand((n, 512), 9, 512 ** -0.5), _rand((n,), 10, 0.1)
     logits = torch.from_numpy(a).double() @ torch.from_numpy(w).double().t() + torch.from_numpy(bias).double()
@@ -103,8 +114,78 @@ def test_vocab_argmax_never_materialises_logits(raw, gemm_kernel, precision, m, 
     assert np.array_equal(ids[clear], logits.argmax(-1).numpy()[clear])
 
 
-def test_vocab_argmax_ties_pick_first_index(raw):
-    # identical weight rows => exactly tied logits; torch.argmax semantics = lowest index
+def _argmax_f64(a, w, bias, chunk=500):
+    """fp64 argmax and top-2 margin, a block of rows at a time (the full logit matrix would be gigabytes)."""
+    wd, bd = torch.from_numpy(w).double().t().contiguous(), torch.from_numpy(bias).double()
+    ids, margin, top = [], [], []
+    for r in range(0, a.shape[0], chunk):
+        lg = torch.from_numpy(a[r:r + chunk]).double() @ wd + bd
+        t2 = lg.topk(2, -1).values
+        ids.append(lg.argmax(-1)); margin.append(t2[:, 0] - t2[:, 1]); top.append(t2[:, 0].abs())
+    return torch.cat(ids).numpy(), torch.cat(margin).numpy(), torch.cat(top).numpy()
+
+
+@pytest.mark.parametrize("m,n", [(9500, 20011), (19000, 5037)])
+def test_vocab_argmax_rescoring_is_fp32_exact(raw, monkeypatch, m, n):
+    """Batches of at least half a wave of 256-row blocks take the candidate path (one-product pass on the A-resident
+    pair kernel, fp32 rescoring of the surviving columns), so the ids must agree with the fp64 argmax wherever the
+    top-2 margin exceeds fp32 rounding — far tighter than the 1e-4 the three-product path is held to — on peaked rows
+    (a planted winner) and flat ones (many near-ties inside the one-product error bound)."""
+    monkeypatch.delenv("FUNASR_B200_VOCAB", raising=False)
+    monkeypatch.delenv("FUNASR_B200_GEMM", raising=False)
+    a, w, bias = _rand((m, 512), 41), _rand((n, 512), 42, 512 ** -0.5), _rand((n,), 43, 0.1)
+    planted = np.random.default_rng(44).choice(n, size=m // 4, replace=False)
+    w[planted] += 0.3 * a[: m // 4] / np.linalg.norm(a[: m // 4], axis=1, keepdims=True)     # clear winners
+    want, margin, top = _argmax_f64(a, w, bias)
+    clear = margin > 2e-6 * np.maximum(top, 1.0)
+    assert clear.mean() > 0.95
+    ids = raw.vocab_argmax(a, w, bias, precision="bf16x3")
+    assert np.array_equal(ids[clear], want[clear])
+    monkeypatch.setenv("FUNASR_B200_GEMM_AR", "0")               # same lists from the general pair kernel's epilogue
+    ids = raw.vocab_argmax(a, w, bias, precision="bf16x3")
+    assert np.array_equal(ids[clear], want[clear])
+
+
+@pytest.mark.parametrize("n", [700, 1100])
+def test_vocab_argmax_overflowing_lists_take_the_second_chance_pass(raw, monkeypatch, n):
+    """Identical weight rows: every column is a candidate, every list overflows, and the gated three-product pass
+    has to produce the ids (lowest index on ties, like torch.argmax); n = 1100 goes through the A-resident kernel."""
+    monkeypatch.delenv("FUNASR_B200_VOCAB", raising=False)
+    monkeypatch.delenv("FUNASR_B200_GEMM", raising=False)
+    m = 9500
+    a = _rand((m, 512), 45)
+    w = np.tile(_rand((1, 512), 46, 512 ** -0.5), (n, 1))
+    bias = np.zeros((n,), np.float32)
+    assert (raw.vocab_argmax(a, w, bias, precision="bf16x3") == 0).all()
+    bias[300] = 1.0
+    bias[650] = 1.0
+    assert (raw.vocab_argmax(a, w, bias, precision="bf16x3") == 300).all()
+    # half of the rows peaked (short lists), half flat (overflow): both kinds in one call
+    w2 = w.copy()
+    w2[17] += 0.5 * a[0] / np.linalg.norm(a[0])
+    a2 = a.copy()
+    a2[: m // 2] = a[0]
+    bias[:] = 0.0
+    ids = raw.vocab_argmax(a2, w2, bias, precision="bf16x3")
+    assert (ids[: m // 2] == 17).all()
+
+
+@pytest.mark.parametrize("m", [300, 9500])
+def test_vocab_argmax_all_logits_negative_last_group_empty(raw, vocab_mode, m):
+    """N = 300: the second 128-column group of the last tile lies wholly past N.  Its partial-maximum slot must not
+    hold stale memory that beats a row whose logits are all negative."""
+    n = 300
+    a, w = _rand((m, 512), 47), _rand((n, 512), 48, 512 ** -0.5)
+    bias = np.full((n,), -50.0, np.float32)
+    want, margin, _ = _argmax_f64(a, w, bias)
+    ids = raw.vocab_argmax(a, w, bias, precision="bf16x3")
+    clear = margin > 1e-4
+    assert np.array_equal(ids[clear], want[clear])
+
+
+def test_vocab_argmax_ties_pick_first_index(raw, vocab_mode):
+    # identical weight rows => exactly tied logits; torch.argmax semantics = lowest index (in the candidate path all
+    # 700 columns are candidates: the lists overflow and the rows are rescored over the whole vocabulary)
     a = _rand((64, 512), 11)
     w = np.tile(_rand((1, 512), 12, 512 ** -0.5), (700, 1))
     bias = np.zeros((700,), np.float32)
