@@ -113,6 +113,7 @@ Context::Context(int device, int max_batch, int64_t max_samples, int precision)
     attention_tc_init_device();
     const char* att = getenv("FUNASR_B200_ATTENTION");     // debugging aid: "simt" keeps fp32 attention in the tensor-core modes
     simt_attention_ = precision == kFp32 || (att && std::string(att) == "simt");
+    if (const char* g = getenv("FUNASR_B200_GRAPH_MAX_BATCH")) graph_max_batch_ = std::max(0, atoi(g));
     t_mel_max_ = (int)(max_samples / kHop + 1);
     t_max_ = lfr_frames_of(max_samples);
     m_max_ = (int64_t)max_batch * t_max_;
@@ -128,6 +129,7 @@ Context::~Context() {
         for (auto& e : it->second.ev) cudaEventDestroy(e);
         g_rings.erase(it);
     }
+    for (auto& kv : graphs_) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     if (h_lens_) cudaFreeHost(h_lens_);
     for (auto& ev : ev_up_) if (ev) cudaEventDestroy(ev);
     if (ev_enc_) cudaEventDestroy(ev_enc_);
@@ -564,7 +566,7 @@ void Context::encode_dev(const float* d_audio, int batch, int64_t s_phys, const 
 }
 
 // a3 onwards: LFR + position -> 70 SAN-M layers -> enc ; adaptor -> adaptor_output
-void Context::encoder_graph(int batch, int64_t s_phys, float* d_enc, float* d_adaptor) {
+void Context::encoder_graph(int batch, int64_t s_phys, float* d_enc, float* d_adaptor, bool record_events) {
     const int t_mel = (int)(s_phys / kHop + 1), frames = lfr_frames_of(s_phys), M = batch * frames;
     tap("logmel", logmel_.as<float>(), (int64_t)batch * t_mel, kMels);
     float* lfr_raw = taps_on_ ? adaptor_out_.as<float>() : nullptr;     // borrowed scratch for the tap
@@ -585,13 +587,52 @@ void Context::encoder_graph(int batch, int64_t s_phys, float* d_enc, float* d_ad
     Planes encpl;
     if (!f32) encpl = Planes{encpl_.as<__nv_bfloat16>(), encpl_.as<__nv_bfloat16>() + m_max_ * kDenc};
     launch_layernorm(x, M, kDenc, tp_g_, tp_b_, 1e-5f, d_tvalid_, frames, d_enc, encpl, stream_);
-    FA_CUDA(cudaEventRecord(ev_enc_, stream_));                          // enc_output is final: a download may start
+    if (record_events) FA_CUDA(cudaEventRecord(ev_enc_, stream_));       // enc_output is final: a download may start
 
     Act in; in.f32 = d_enc; in.pl = encpl; in.ld = kDenc;
     projector(adaptor_, in, batch, frames, d_tvalid_);
     launch_row_keep(x, d_adaptor, batch, frames, kDllm, d_tlen_, stream_);
-    FA_CUDA(cudaEventRecord(ev_ad_, stream_));
+    if (record_events) FA_CUDA(cudaEventRecord(ev_ad_, stream_));
 }
+
+// ------------------------------------------------------------------------------------ graph replay
+bool Context::use_graph(int batch) const { return batch <= graph_max_batch_ && !g_prof_on && !taps_on_; }
+
+// Runs `body` (kernel launches on stream_ only, no host synchronisation) as a CUDA graph: captured and instantiated
+// the first time a (kind, batch, size) is seen, replayed afterwards.  Every pointer a launch carries is a workspace
+// or weight address of this context and the per-call lengths are read from device memory, so a replay is exact.
+template <class F>
+void Context::run_graphed(int kind, int batch, int64_t size, F&& body) {
+    const auto key = std::make_tuple(kind, batch, size);
+    auto it = graphs_.find(key);
+    if (it == graphs_.end()) {
+        if (graphs_.size() >= 32) {                      // odd lengths every call: do not hoard executables
+            for (auto& kv : graphs_) cudaGraphExecDestroy(kv.second.exec);
+            graphs_.clear();
+        }
+        const int64_t before = g_launches;
+        FA_CUDA(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+        cudaGraph_t graph = nullptr;
+        try {
+            body();
+        } catch (...) {
+            cudaStreamEndCapture(stream_, &graph);
+            if (graph) cudaGraphDestroy(graph);
+            throw;
+        }
+        FA_CUDA(cudaStreamEndCapture(stream_, &graph));
+        GraphEntry ge;
+        ge.launches = g_launches - before;
+        g_launches = before;                             // nothing has run yet; the launch below counts them
+        const cudaError_t e = cudaGraphInstantiate(&ge.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        FA_CUDA(e);
+        it = graphs_.emplace(key, ge).first;
+    }
+    FA_CUDA(cudaGraphLaunch(it->second.exec, stream_));
+    g_launches += it->second.launches;
+}
+
 
 void Context::ctc_dev(const float* d_enc, int batch, int frames, int32_t* d_ids) {
     FA_REQUIRE(finalized_, "context not finalized");
@@ -699,7 +740,8 @@ void Context::ctc_host(const float* enc, int batch, int frames, int32_t* ids) {
     for (int b0 = 0; b0 < batch; b0 += max_batch_) {
         const int nb = std::min(max_batch_, batch - b0);
         FA_CUDA(cudaMemcpyAsync(enc_.p, enc + (size_t)b0 * frames * kDenc, (size_t)nb * frames * kDenc * 4, cudaMemcpyHostToDevice, stream_));
-        ctc_dev(enc_.as<float>(), nb, frames, ids_.as<int32_t>());
+        if (use_graph(nb)) run_graphed(2, nb, frames, [&] { ctc_dev(enc_.as<float>(), nb, frames, ids_.as<int32_t>()); });
+        else ctc_dev(enc_.as<float>(), nb, frames, ids_.as<int32_t>());
         FA_CUDA(cudaMemcpyAsync(ids + (size_t)b0 * frames, ids_.p, (size_t)nb * frames * 4, cudaMemcpyDeviceToHost, stream_));
         FA_CUDA(cudaStreamSynchronize(stream_));
     }
@@ -714,6 +756,21 @@ void Context::front_half_host(const float* audio, int batch, int64_t s_phys, con
     for (int b0 = 0; b0 < batch; b0 += max_batch_) {
         const int nb = std::min(max_batch_, batch - b0);
         stage_lengths(nb, s_phys, ilens + b0);
+        if (use_graph(nb)) {
+            // launch-bound regime: one upload, one graph (front end, encoder, adaptor and, if asked for, the CTC head),
+            // downloads behind it on the same stream
+            FA_CUDA(cudaMemcpyAsync(audio_.p, audio + (size_t)b0 * s_phys, (size_t)nb * s_phys * 4, cudaMemcpyHostToDevice, stream_));
+            run_graphed(ids ? 1 : 0, nb, s_phys, [&] {
+                front_end(audio_.as<float>(), 0, nb, s_phys);
+                encoder_graph(nb, s_phys, enc_.as<float>(), adaptor_out_.as<float>(), false);
+                if (ids) ctc_dev(enc_.as<float>(), nb, frames, ids_.as<int32_t>());
+            });
+            if (enc) FA_CUDA(cudaMemcpyAsync(enc + (size_t)b0 * frames * kDenc, enc_.p, (size_t)nb * frames * kDenc * 4, cudaMemcpyDeviceToHost, stream_));
+            if (adaptor) FA_CUDA(cudaMemcpyAsync(adaptor + (size_t)b0 * frames * kDllm, adaptor_out_.p, (size_t)nb * frames * kDllm * 4, cudaMemcpyDeviceToHost, stream_));
+            if (ids) FA_CUDA(cudaMemcpyAsync(ids + (size_t)b0 * frames, ids_.p, (size_t)nb * frames * 4, cudaMemcpyDeviceToHost, stream_));
+            FA_CUDA(cudaStreamSynchronize(stream_));
+            continue;
+        }
         upload_and_front_end(audio + (size_t)b0 * s_phys, nb, s_phys);
         encoder_graph(nb, s_phys, enc_.as<float>(), adaptor_out_.as<float>());
         if (enc) download_async(enc + (size_t)b0 * frames * kDenc, enc_.p, (size_t)nb * frames * kDenc * 4, ev_enc_);

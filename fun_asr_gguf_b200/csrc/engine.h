@@ -4,6 +4,7 @@
 #include "kernels.h"
 
 #include <map>
+#include <tuple>
 #include <memory>
 #include <string>
 #include <vector>
@@ -115,7 +116,11 @@ private:
     // encode_dev in three parts, so that the host variants can overlap copies with the front end
     void stage_lengths(int batch, int64_t s_phys, const int64_t* h_ilens);
     void front_end(const float* d_audio, int b0, int nb, int64_t s_phys);
-    void encoder_graph(int batch, int64_t s_phys, float* d_enc, float* d_adaptor);
+    void encoder_graph(int batch, int64_t s_phys, float* d_enc, float* d_adaptor, bool record_events = true);
+    // Small batches are launch-bound (some 620 launches per 60 s segment against a few milliseconds of GPU work):
+    // the host variants replay them as CUDA graphs, captured once per (call kind, batch, samples).
+    bool use_graph(int batch) const;
+    template <class F> void run_graphed(int kind, int batch, int64_t size, F&& body);
     void upload_and_front_end(const float* audio_host, int nb, int64_t s_phys);
     void download_async(void* host, const void* dev, size_t bytes, cudaEvent_t after);
     Planes qkv_planes() const;
@@ -159,6 +164,9 @@ private:
     int* d_tlen_ = nullptr;
     int* h_lens_ = nullptr;      // pinned staging for the three length vectors
     int logits_rows_ = 0;
+    struct GraphEntry { cudaGraphExec_t exec = nullptr; int64_t launches = 0; };
+    std::map<std::tuple<int, int, int64_t>, GraphEntry> graphs_;
+    int graph_max_batch_ = 4;                 // FUNASR_B200_GRAPH_MAX_BATCH (0 turns graph replay off)
     std::map<std::string, std::pair<std::vector<int64_t>, std::unique_ptr<DevBuf>>> taps_;
 };
 

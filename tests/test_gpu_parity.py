@@ -119,6 +119,35 @@ def test_runs_are_bit_reproducible(engine):
         assert np.array_equal(x, y)
 
 
+def test_graph_replay_is_bit_identical_to_eager_launches(weights, monkeypatch):
+    """Batches of up to FUNASR_B200_GRAPH_MAX_BATCH (4) segments are replayed as CUDA graphs by the host variants
+    (fa_encode / fa_ctc / fa_front_half).  A replay must give exactly what eager launches give, with the per-call
+    lengths (read from device memory, not baked into the graph) changing between replays of one graph."""
+    s = 3 * SR
+    x = np.stack([signals.structured(s, 31).numpy(), signals.white(s, 32).numpy()])
+    calls = [[s, s], [s - 4001, 2 * SR + 17], [s, s], [777, s - 1]]
+    graphed = FrontHalf(weights, device=0, max_batch=2, max_samples=s, precision="bf16x3")
+    monkeypatch.setenv("FUNASR_B200_GRAPH_MAX_BATCH", "0")
+    eager = FrontHalf(weights, device=0, max_batch=2, max_samples=s, precision="bf16x3")
+    try:
+        for lens in calls:
+            n0 = graphed.launch_count()
+            g = graphed.front_half(x, lens)
+            n1 = graphed.launch_count()
+            e = eager.front_half(x, lens)
+            n2 = eager.launch_count()
+            for a, b in zip(g, e):
+                assert np.array_equal(a, b)
+            assert n1 - n0 > 600 and n2 - n1 > 600     # a replay counts the kernels it contains
+            # the two-session form: encoder graph, then CTC graph on the downloaded enc_output
+            enc, ad = graphed.encode(x, lens)
+            assert np.array_equal(enc, e[0]) and np.array_equal(ad, e[1])
+            assert np.array_equal(graphed.ctc(enc), e[2])
+    finally:
+        graphed.close()
+        eager.close()
+
+
 def test_planted_projection_token_exact(weights, planted_weights, consts, golden):
     """F11: with plain random init the ids barely vary; the planted CTC projection makes them change
     every few frames with runs and blanks, so token-exactness and collapse are really exercised."""
