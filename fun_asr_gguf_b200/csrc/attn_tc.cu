@@ -43,6 +43,9 @@
 #include "kernels.h"
 #include "tc_ptx.cuh"
 
+#include <cstdlib>
+#include <vector>
+
 namespace fa {
 
 namespace {
@@ -51,6 +54,7 @@ constexpr int QT = 128;          // queries per item (UMMA M)
 constexpr int KT = 128;          // keys per tile (UMMA N for S, K extent for PV)
 constexpr int kAttThreads = 704;
 constexpr int kSlots = 6;
+constexpr bool kAttnTiming = false;   // tuning aid: set true, rebuild, run with FUNASR_B200_ATTN_TIMING=1 (per-cause wait cycles of the MMA warp)
 
 template <int DK> struct ACfg {
     static constexpr int kChunks = DK / 64;                  // 128-byte column chunks per head row
@@ -78,6 +82,7 @@ struct AttnParams {
     __nv_bfloat16* ctx_hi;
     __nv_bfloat16* ctx_lo;
     int ldo;
+    long long* dbg;                            // tuning aid (FUNASR_B200_ATTN_TIMING): cycles the MMA warp waits, by cause
 };
 
 template <int DK>
@@ -92,10 +97,11 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
     const uint32_t bar_kvfull = bars, bar_kvempty = bars + 8 * kSlots;   // [kSlots] each
     const uint32_t bar_sfull = bars + 16 * kSlots, bar_sempty = bar_sfull + 16;   // [2] each
     const uint32_t bar_pfull = bar_sempty + 16;                          // [2]
-    const uint32_t bar_qfull = bar_pfull + 16, bar_qempty = bar_qfull + 8;
+    const uint32_t bar_qfull = bar_pfull + 16, bar_qempty = bar_qfull + 8;   // hi plane of Q in TMEM (all pass 1 needs)
     const uint32_t bar_ofull = bar_qempty + 8, bar_oempty = bar_ofull + 8;
     const uint32_t bar_lfull = bar_oempty + 8;                           // [2]
-    const uint32_t tmem_slot = bar_lfull + 16;
+    const uint32_t bar_qlofull = bar_lfull + 16;                         // lo plane of Q in TMEM (first needed by pass 2)
+    const uint32_t tmem_slot = bar_qlofull + 8;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
     float* l_smem = reinterpret_cast<float*>(smem_raw + (l_base - raw));
     float* mx_smem = l_smem + 8 * QT;
@@ -111,7 +117,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
             mbar_init(bar_pfull + 8 * s, 8);
             mbar_init(bar_lfull + 8 * s, 16);
         }
-        mbar_init(bar_qfull, 4); mbar_init(bar_qempty, 1);
+        mbar_init(bar_qfull, 4); mbar_init(bar_qlofull, 4); mbar_init(bar_qempty, 1);
         mbar_init(bar_ofull, 1); mbar_init(bar_oempty, 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_async_smem();
@@ -182,6 +188,17 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
         uint32_t item_it = 0;
         uint32_t slot = 0, slot_ph = 0;                             // next ring slot and its fill parity
         uint32_t se0 = 0, se1 = 0, pf0 = 0, pf1 = 0;                // per score tile: waits so far on "scores consumed" / "weights ready"
+        long long dbg_c[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        long long tph = 0;
+        auto tic = [&]() { if (kAttnTiming && p.dbg) tph = clock64(); };
+        auto toc = [&](int cat) { if (kAttnTiming && p.dbg) dbg_c[cat] += clock64() - tph; };
+        auto twait = [&](int cat, uint32_t bar, uint32_t parity) {           // mbar_wait, timed when p.dbg is set
+            if (!kAttnTiming || !p.dbg) { mbar_wait(bar, parity); return; }
+            const long long t0 = clock64();            // try_wait itself may block for a while: time all of it
+            mbar_wait(bar, parity);
+            dbg_c[cat] += clock64() - t0;
+        };
+        const long long dbg_t0 = kAttnTiming ? clock64() : 0;
         auto take = [&](uint32_t& s_out, uint32_t& ph_out) {
             s_out = slot; ph_out = slot_ph;
             if (++slot == kSlots) { slot = 0; slot_ph ^= 1; }
@@ -205,32 +222,35 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
         for (int item = blockIdx.x; item < items; item += gridDim.x, ++item_it) {
             int b, h, qt, n, klen;
             decode(item, b, h, qt, n, klen);
-            mbar_wait(bar_qfull, item_it & 1);                      // this item's Q is in TMEM
+            twait(0, bar_qfull, item_it & 1);                       // this item's Q is in TMEM
             // ---- pass 1: shift = max of the hi*hi scores.  Tiles 0, 1 follow the previous item's P V in issue order;
             // later tiles wait until the softmax group has read the scores they overwrite.
             for (int j = 0; j < n; ++j) {
                 const uint32_t buf = j & 1;
                 uint32_t s0, p0;
                 take(s0, p0);
-                mbar_wait(bar_kvfull + 8 * s0, p0);
-                if (j >= 2) { uint32_t& se = buf ? se1 : se0; mbar_wait(bar_sempty + 8 * buf, se & 1); ++se; }
+                twait(1, bar_kvfull + 8 * s0, p0);
+                if (j >= 2) { uint32_t& se = buf ? se1 : se0; twait(2, bar_sempty + 8 * buf, se & 1); ++se; }
                 tc_fence_after();
+                tic();
                 if (elect_one()) {
                     s_term(tmem_base + C::kSCol + buf * KT, tmem_q, kv_base + s0 * C::kSlotBytes, 0u);
                     tc_commit(bar_sfull + 8 * buf);
                     tc_commit(bar_kvempty + 8 * s0);
                 }
                 __syncwarp();
+                toc(12);
             }
             // ---- pass 2.  S(0), S(1) wait for the last pass-1 scores of their tile to be read; after that S(j+2)
             // follows P(j) V(j) in issue order and needs no barrier of its own.
             uint32_t ka, kpa, kb, kpb;                              // ring slots of the S about to be issued (K hi, K lo)
+            twait(15, bar_qlofull, item_it & 1);                    // the lo plane of Q landed during pass 1
             for (int j = 0; j < 2 && j < n; ++j) {
                 const uint32_t buf = j;
                 take(ka, kpa); take(kb, kpb);
-                mbar_wait(bar_kvfull + 8 * ka, kpa);
-                mbar_wait(bar_kvfull + 8 * kb, kpb);
-                { uint32_t& se = buf ? se1 : se0; mbar_wait(bar_sempty + 8 * buf, se & 1); ++se; }
+                twait(3, bar_kvfull + 8 * ka, kpa);
+                twait(3, bar_kvfull + 8 * kb, kpb);
+                { uint32_t& se = buf ? se1 : se0; twait(4, bar_sempty + 8 * buf, se & 1); ++se; }
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t tile = tmem_base + C::kSCol + buf * KT;
@@ -247,10 +267,10 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
             // barriers of P(0) V(0): V hi, V lo, the weights, a drained O
             uint32_t va, vpa, vb, vpb;
             take(va, vpa); take(vb, vpb);
-            mbar_wait(bar_oempty, (item_it & 1) ^ 1);
-            mbar_wait(bar_kvfull + 8 * va, vpa);
-            mbar_wait(bar_kvfull + 8 * vb, vpb);
-            mbar_wait(bar_pfull, pf0 & 1);
+            twait(5, bar_oempty, (item_it & 1) ^ 1);
+            twait(6, bar_kvfull + 8 * va, vpa);
+            twait(6, bar_kvfull + 8 * vb, vpb);
+            twait(7, bar_pfull, pf0 & 1);
             ++pf0;
             for (int j = 0; j < n; ++j) {
                 const uint32_t buf = j & 1;
@@ -260,9 +280,10 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
                 bool k_ready = true;
                 if (s_next) { take(ka, kpa); take(kb, kpb); }
                 tc_fence_after();
+                tic();
                 if (elect_one()) pv_term(tile, 16, kv_base + va * C::kSlotBytes, j ? 1u : 0u);
                 __syncwarp();
-                if (s_next) k_ready = mbar_try_wait(bar_kvfull + 8 * ka, kpa) & mbar_try_wait(bar_kvfull + 8 * kb, kpb);
+                if (s_next) k_ready = mbar_test(bar_kvfull + 8 * ka, kpa) & mbar_test(bar_kvfull + 8 * kb, kpb);
                 if (elect_one()) {
                     pv_term(tile, 0, kv_base + vb * C::kSlotBytes, 1u);
                     pv_term(tile, 0, kv_base + va * C::kSlotBytes, 1u);
@@ -271,18 +292,20 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
                     if (j == n - 1) tc_commit(bar_ofull);
                 }
                 __syncwarp();
+                toc(13);
                 // ---- S(j+2) over the tile P(j) was in; in its middle, poll the barriers of P(j+1) V(j+1)
                 bool v_ready = true;
                 const uint32_t nbuf = buf ^ 1;
                 uint32_t& pfn = nbuf ? pf1 : pf0;
                 if (pv_next) { take(va, vpa); take(vb, vpb); }
                 if (s_next) {
-                    if (!k_ready) { mbar_wait(bar_kvfull + 8 * ka, kpa); mbar_wait(bar_kvfull + 8 * kb, kpb); }
+                    if (!k_ready) { twait(8, bar_kvfull + 8 * ka, kpa); twait(8, bar_kvfull + 8 * kb, kpb); }
                     tc_fence_after();
+                    tic();
                     if (elect_one()) s_term(tile, tmem_q + C::kQPlaneCols, kv_base + ka * C::kSlotBytes, 0u);
                     __syncwarp();
-                    v_ready = mbar_try_wait(bar_kvfull + 8 * va, vpa) & mbar_try_wait(bar_kvfull + 8 * vb, vpb) &
-                              mbar_try_wait(bar_pfull + 8 * nbuf, pfn & 1);
+                    v_ready = mbar_test(bar_kvfull + 8 * va, vpa) & mbar_test(bar_kvfull + 8 * vb, vpb) &
+                              mbar_test(bar_pfull + 8 * nbuf, pfn & 1);
                     if (elect_one()) {
                         s_term(tile, tmem_q, kv_base + kb * C::kSlotBytes, 1u);
                         s_term(tile, tmem_q, kv_base + ka * C::kSlotBytes, 1u);
@@ -292,18 +315,23 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
                         if (j + 3 == n) tc_commit(bar_qempty);
                     }
                     __syncwarp();
+                    toc(14);
                 } else {
                     v_ready = false;
                 }
                 if (pv_next) {
                     if (!v_ready) {
-                        mbar_wait(bar_kvfull + 8 * va, vpa);
-                        mbar_wait(bar_kvfull + 8 * vb, vpb);
-                        mbar_wait(bar_pfull + 8 * nbuf, pfn & 1);
+                        twait(9, bar_kvfull + 8 * va, vpa);
+                        twait(9, bar_kvfull + 8 * vb, vpb);
+                        twait(10, bar_pfull + 8 * nbuf, pfn & 1);
                     }
                     ++pfn;
                 }
             }
+        }
+        if (kAttnTiming && p.dbg && lane == 0) {
+            dbg_c[11] = clock64() - dbg_t0;
+            for (int i = 0; i < 16; ++i) p.dbg[blockIdx.x * 16 + i] = dbg_c[i];
         }
     } else if (warp < 18) {
         // ================================================================== softmax (4 groups of 4 warps)
@@ -319,7 +347,8 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
             int b, h, qt, n, klen;
             decode(item, b, h, qt, n, klen);
             float mx = -INFINITY;
-            // ---- pass 1
+            // ---- pass 1 (sharing every tile among all sixteen warps, 32 keys each, was measured and is slower: the
+            // fixed cost of a hand-off per tile per warp outweighs the shorter read)
             for (int j = grp; j < n; j += 2, ++su) {
                 mbar_wait(sfull, su & 1);
                 tc_fence_after();
@@ -330,8 +359,14 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
                     tc_ld32(tmem_s + c * 32, s);
                     tc_wait_ld();
                     if (kbase + c * 32 + 32 <= klen) {
+                        float m4[4] = {mx, -INFINITY, -INFINITY, -INFINITY};      // four short chains instead of one of 16
 #pragma unroll
-                        for (int i = 0; i < 32; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(s[i]), __uint_as_float(s[i + 1])));
+                        for (int i = 0; i < 32; i += 8) {
+#pragma unroll
+                            for (int a = 0; a < 4; ++a)
+                                m4[a] = fmaxf(m4[a], fmaxf(__uint_as_float(s[i + 2 * a]), __uint_as_float(s[i + 2 * a + 1])));
+                        }
+                        mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
                     } else {
 #pragma unroll
                         for (int i = 0; i < 32; ++i)
@@ -389,42 +424,58 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
         const int quarter = warp & 3;
         const int r = quarter * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-        // Q rows of one item, both planes, global -> registers -> TMEM columns kQCol..: word c of a plane = elements 2c, 2c+1
-        auto load_q = [&](int item) {
+        // Q rows of one item, global -> registers -> TMEM columns kQCol..: word c of a plane = elements 2c, 2c+1.
+        // The hi plane of the NEXT item is fetched into registers before the current item's last S product has
+        // retired (the loads do not touch TMEM), so that once Q's columns are free only the stores are left before
+        // pass 1 can start; the lo plane, which pass 2 needs some thousand cycles later, follows.
+        constexpr int kQW = DK / 2;                                 // 32-bit words per row per plane
+        auto q_src = [&](int item, int pl, bool& ok) -> const uint4* {
             int b, h, qt, n, klen;
             decode(item, b, h, qt, n, klen);
             const int row = qt * QT + r;
-            const bool ok = row < p.frames;
+            ok = row < p.frames;
             const int64_t off = ((int64_t)b * p.frames + row) * p.ld + h * DK;
+            return reinterpret_cast<const uint4*>((pl ? p.q_lo : p.q_hi) + off);
+        };
+        auto q_fetch = [&](int item, int pl, uint32_t (&w)[kQW]) {
+            bool ok;
+            const uint4* src = q_src(item, pl, ok);
 #pragma unroll
-            for (int pl = 0; pl < 2; ++pl) {
-                const uint4* src = reinterpret_cast<const uint4*>((pl ? p.q_lo : p.q_hi) + off);
+            for (int i = 0; i < kQW / 4; ++i) {
+                const uint4 v = ok ? __ldg(src + i) : make_uint4(0u, 0u, 0u, 0u);
+                w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+            }
+        };
+        auto q_store = [&](int pl, const uint32_t (&w)[kQW], uint32_t bar) {
 #pragma unroll
-                for (int g = 0; g < DK / 64; ++g) {                 // 32 words = 64 elements per store
-                    uint32_t w[32];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const uint4 v = ok ? __ldg(src + g * 8 + i) : make_uint4(0u, 0u, 0u, 0u);
-                        w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
-                    }
-                    tc_st32(tmem_base + lane_addr + C::kQCol + pl * C::kQPlaneCols + g * 32, w);
-                }
+            for (int g = 0; g < kQW / 32; ++g) {
+                tc_st32(tmem_base + lane_addr + C::kQCol + pl * C::kQPlaneCols + g * 32,
+                        *reinterpret_cast<const uint32_t(*)[32]>(&w[g * 32]));
             }
             tc_wait_st();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_qfull);
+            if (lane == 0) mbar_arrive(bar);
         };
         uint32_t item_it = 0;
-        if ((int)blockIdx.x < items) load_q(blockIdx.x);
+        uint32_t qw[kQW];
+        if ((int)blockIdx.x < items) {
+            q_fetch(blockIdx.x, 0, qw);
+            q_store(0, qw, bar_qfull);
+            q_fetch(blockIdx.x, 1, qw);
+            q_store(1, qw, bar_qlofull);
+        }
         for (int item = blockIdx.x; item < items; item += gridDim.x, ++item_it) {
             int b, h, qt, n, klen;
             decode(item, b, h, qt, n, klen);
             const int next = item + gridDim.x;
             if (next < items) {
+                q_fetch(next, 0, qw);                               // in flight while this item's S products finish
                 mbar_wait(bar_qempty, item_it & 1);                 // every S product of this item has retired
                 tc_fence_after();
-                load_q(next);
+                q_store(0, qw, bar_qfull);
+                q_fetch(next, 1, qw);
+                q_store(1, qw, bar_qlofull);
             }
             // ---- epilogue: O / l
             mbar_wait(bar_ofull, item_it & 1);
@@ -502,11 +553,28 @@ void launch_attention_tc(Planes qkv, int64_t plane_stride, int ld, int d_model, 
     p.ctx = ctx_f32; p.ctx_hi = ctx_pl.hi; p.ctx_lo = ctx_pl.lo; p.ldo = ldo;
     const int items = batch * heads * cdiv(frames, QT);
     const int grid = items < g_att_sms ? items : g_att_sms;
+    static const bool timing = kAttnTiming && getenv("FUNASR_B200_ATTN_TIMING") != nullptr;
+    long long* dbg = nullptr;
+    if (timing) { FA_CUDA(cudaMalloc(&dbg, (size_t)grid * 16 * sizeof(long long))); p.dbg = dbg; }
     prof_note_work(4.0 * batch * heads * (double)frames * frames * dk, 0.0);
     if (dk == 128) {
         FA_LAUNCH(k_attention_tc<128>, grid, kAttThreads, ACfg<128>::kSmemBytes, st, mkv.map, p);
     } else {
         FA_LAUNCH(k_attention_tc<64>, grid, kAttThreads, ACfg<64>::kSmemBytes, st, mkv.map, p);
+    }
+    if (timing) {       // tuning aid only: synchronises
+        std::vector<long long> h((size_t)grid * 16);
+        FA_CUDA(cudaStreamSynchronize(st));
+        FA_CUDA(cudaMemcpy(h.data(), dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        FA_CUDA(cudaFree(dbg));
+        double c[16] = {0};
+        for (int b = 0; b < grid; ++b)
+            for (int i = 0; i < 16; ++i) c[i] += (double)h[(size_t)b * 16 + i] / grid;
+        static const char* names[16] = {"qfull", "p1 K", "p1 sempty", "p2 S01 K", "p2 S01 sempty", "oempty", "first V", "first P",
+                                        "loop K", "loop V", "loop P", "total", "issue p1 S", "issue PV", "issue S", "qlo"};
+        fprintf(stderr, "attention MMA-warp waits (mean cycles per CTA, %d items over %d CTAs, dk %d):", items, grid, dk);
+        for (int i = 0; i < 16; ++i) fprintf(stderr, " %s=%.0f", names[i], c[i]);
+        fprintf(stderr, "\n");
     }
 }
 

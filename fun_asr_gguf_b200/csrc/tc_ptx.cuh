@@ -41,6 +41,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Non-blocking probe.  mbarrier.try_wait may suspend the thread for a system-dependent time when the phase is not
+// complete, which is the wrong thing for a poll placed between two groups of tcgen05.mma (the pipe queues only a few
+// instructions ahead of the issuing thread); test_wait returns at once.
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 // Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU.  The retry loop (with its
 // clock reads and the diagnostic) is kept out of line so that a wait that succeeds at once costs one instruction.
 __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {

@@ -234,9 +234,135 @@ __global__ void __launch_bounds__(128, 1) k_attn_pattern(int alias, int tiles, l
     }
 }
 
+// The same pass-2 issue pattern while other agents use the SM as in attn_tc.cu: (flags & 1) one warp streams bulk
+// copies global -> shared memory (what the K/V ring does: 128 KB per key tile in the kernel), (flags & 2) 16 warps
+// read and write 32-column chunks of the score tiles (tcgen05.ld / tcgen05.st, what the softmax warps do).
+// out[0] = cycles of the MMA stream, out[1] = bytes copied while it ran, out[2] = ld+st chunk pairs done.
+__global__ void __launch_bounds__(576, 1) k_attn_traffic(int flags, int tiles, int pace, const unsigned char* gsrc, long long* out) {
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ uint64_t bar, cbar[4];
+    __shared__ uint32_t tmem_slot;
+    __shared__ volatile int done;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+        for (int i = 0; i < 4; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&cbar[i])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        done = 0;
+    }
+    for (int i = threadIdx.x; i < 66 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem_raw)[i] = 0x3c003c00u;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_slot, 0);
+    if (warp == 0) {
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t idesc_mn = idesc | (1u << 16);
+        const long long t0 = clock64();
+        for (int j = 0; j < tiles; ++j) {
+            const uint32_t s_tile = tmem + (uint32_t)(j & 1) * 128u, o_tile = tmem + 256u;
+            if (elect_one()) {
+#pragma unroll
+                for (int i = 0; i < 24; ++i)
+                    mma_ts(o_tile, s_tile + (uint32_t)((i & 7) >> 1) * 32u + (uint32_t)(i & 1) * 8u,
+                           umma_desc(base + (uint32_t)(i & 7) * 2048u, 16384, 1024), idesc_mn, (j | i) ? 1u : 0u);
+#pragma unroll
+                for (int i = 0; i < 24; ++i)
+                    mma_ts(s_tile, tmem + 384u + (uint32_t)(i & 7) * 8u,
+                           umma_desc(base + 32768 + (uint32_t)((i & 7) >> 2) * 16384u + (uint32_t)(i & 3) * 32u, 16, 1024), idesc, i ? 1u : 0u);
+            }
+            __syncwarp();
+        }
+        if (elect_one())
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+        __syncwarp();
+        uint32_t ok = 0;
+        while (!ok) {
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                         : "=r"(ok) : "r"(smem_u32(&bar)), "r"(0u) : "memory");
+        }
+        const long long t1 = clock64();
+        done = 1;
+        if (blockIdx.x == 0 && lane == 0) out[0] = t1 - t0;
+    } else if (warp == 1) {
+        if ((flags & 1) && lane == 0) {
+            // 4 copies of 32 KB in flight into a 128 KB region above the operands; optionally paced to `pace` cycles per copy
+            long long bytes = 0;
+            uint32_t ph[4] = {0, 0, 0, 0};
+            const unsigned char* src = gsrc + (size_t)blockIdx.x * (1u << 20);
+            int it = 0;
+            long long next = clock64();
+            for (int i = 0; i < 4; ++i, ++it) {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&cbar[i])), "r"(32768u) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(base + 66 * 1024 + i * 32768), "l"(src + (size_t)(it & 31) * 32768), "r"(32768u), "r"(smem_u32(&cbar[i])) : "memory");
+            }
+            while (!done) {
+                const int i = it & 3;
+                uint32_t ok = 0;
+                while (!ok)
+                    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                                 : "=r"(ok) : "r"(smem_u32(&cbar[i])), "r"(ph[i]) : "memory");
+                ph[i] ^= 1;
+                bytes += 32768;
+                if (pace) { next += pace; while (clock64() < next) {} }
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&cbar[i])), "r"(32768u) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(base + 66 * 1024 + i * 32768), "l"(src + (size_t)(it & 31) * 32768), "r"(32768u), "r"(smem_u32(&cbar[i])) : "memory");
+                ++it;
+            }
+            for (int i = 0; i < 4; ++i) {            // drain
+                uint32_t ok = 0;
+                while (!ok)
+                    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                                 : "=r"(ok) : "r"(smem_u32(&cbar[(it + i) & 3])), "r"(ph[(it + i) & 3]) : "memory");
+            }
+            if (blockIdx.x == 0) out[1] = bytes;
+        }
+    } else if (flags & 2) {
+        const int g = warp - 2;                                    // 16 warps: lane quarter warp & 3, 64-column slice g >> 2
+        const uint32_t ta = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(g >> 2) * 64u;
+        long long n = 0;
+        uint32_t acc = 0;
+        while (!done) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t r[32];
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                               "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                             : "r"(ta + c * 32) : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int i = 0; i < 32; ++i) { acc += r[i]; r[i] = (r[i] & 0x3fff3fffu) | 0x3c003c00u; }
+                asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+                             ::"r"(ta + c * 32), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+                               "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            if (pace) { const long long t = clock64(); while (clock64() - t < pace / 4) {} }
+            ++n;
+        }
+        if (acc == 0x12345u) out[3] = acc;
+        if (blockIdx.x == 0 && threadIdx.x == 64) out[2] = n;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    }
+}
+
 int main() {
     long long* d_out;
-    cudaMalloc(&d_out, 16);
+    cudaMalloc(&d_out, 64);
     cudaFuncSetAttribute(k_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 66 * 1024);
     const int iters = 4096;
     for (int warm = 0; warm < 2; ++warm)
@@ -287,5 +413,25 @@ int main() {
             printf("queue: %2d MMAs (N=256, %4d cycles) then a %6.1f-cycle chain : %7.1f cycles per group\n", group, group * 128,
                    (double)base_cyc / groups, (double)cyc / groups);
         }
+    {
+        unsigned char* gsrc;
+        cudaMalloc(&gsrc, (size_t)148 << 20);
+        cudaMemset(gsrc, 0x3c, (size_t)148 << 20);
+        cudaFuncSetAttribute(k_attn_traffic, cudaFuncAttributeMaxDynamicSharedMemorySize, (66 + 128 + 2) * 1024);
+        for (int pace : {0, 768})
+            for (int flags : {0, 1, 2, 3}) {
+                long long h[4] = {0, 0, 0, 0};
+                for (int rep = 0; rep < 2; ++rep) {
+                    cudaMemset(d_out, 0, 32);
+                    k_attn_traffic<<<148, 576, (66 + 128 + 2) * 1024>>>(flags, 256, pace, gsrc, d_out);
+                    cudaError_t e = cudaDeviceSynchronize();
+                    if (e != cudaSuccess) printf("traffic kernel: %s\n", cudaGetErrorString(e));
+                    cudaMemcpy(h, d_out, 32, cudaMemcpyDeviceToHost);
+                }
+                printf("attention pattern + %s%s%s (%s): %7.1f cycles per key tile (ideal 3072), %.0f KB copied and %.1f ld/st chunk pairs per warp per tile\n",
+                       flags & 1 ? "bulk copies into smem" : "", flags == 3 ? " + " : "", flags & 2 ? "16 warps of tcgen05.ld/st" : (flags ? "" : "nothing"),
+                       pace ? "paced like the kernel" : "flat out", (double)h[0] / 256, (double)h[1] / 256 / 1024, 2.0 * (double)h[2] / 256);
+            }
+    }
     return 0;
 }
