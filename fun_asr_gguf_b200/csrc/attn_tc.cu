@@ -11,11 +11,17 @@
 // softmax weights p are all carried as bf16 hi/lo planes and every product is hi*hi + hi*lo + lo*hi
 // into an fp32 TMEM accumulator, like the projections.  The softmax itself is fp32.
 //
-// Two passes over the keys instead of an online rescale.  Pass 1 only needs a shift that keeps exp2 in
-// range, not the exact row maximum (softmax is invariant to the shift), so it runs ONE product,
-// q_hi k_hi^T, and loads only the hi plane of K.  Pass 2 computes S with all three products, forms
-// p = exp2(S - shift) and accumulates O = sum p v in TMEM with no correction step.  Tensor work per key
-// tile: 1 + 3 + 3 units instead of the 6 + rescale of an online softmax in this precision.
+// No online rescale.  The softmax is invariant to the shift subtracted from the scores, so the shift only has to keep
+// exp2 in range, and an item (segment, head, 128-query tile) runs in one of two modes:
+//   fast   the shift of a row is the maximum of its exact scores over key tile 0 (the first 128 keys).  One pass:
+//          S = three products, p = exp2(S - shift), O += P V.  A later key may beat that shift; the weights then
+//          exceed 1, which fp32 carries up to 2^127.  A row whose sum of weights passes 2^60 marks the item ...
+//   exact  ... and marked items are repeated after the CTA's other items (every role walks the same sequence, a
+//          CTA-wide barrier in between) with the shift taken over ALL keys by a first pass that runs ONE product,
+//          q_hi k_hi^T, and loads only the hi plane of K.  Tensor work per key tile: 1 + 3 + 3 units.
+// Measured on one B200 (tools/attn_bench.py, 32 x 4 heads x 1001 frames): exact everywhere 200 us, fast 181 us; the
+// repeat needs a key that outscores the first 128 by 60 in log2 units, which the parity cases never produce and a
+// kernel test plants on purpose.
 //
 // Shapes follow what the tensor core was measured to sustain on B200 (tools/umma_bench.cu, cycles per
 // M128 x N x K16 bf16 instruction): A from shared memory 83 / 97 / 161 for N = 64 / 128 / 256, A from
@@ -44,6 +50,7 @@
 #include "tc_ptx.cuh"
 
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 namespace fa {
@@ -54,12 +61,13 @@ constexpr int QT = 128;          // queries per item (UMMA M)
 constexpr int KT = 128;          // keys per tile (UMMA N for S, K extent for PV)
 constexpr int kAttThreads = 704;
 constexpr int kSlots = 6;
+constexpr int kRedoWords = 64;       // one bit per item of a CTA's sequence (2048 items per CTA)
 constexpr bool kAttnTiming = false;   // tuning aid: set true, rebuild, run with FUNASR_B200_ATTN_TIMING=1 (per-cause wait cycles of the MMA warp)
 
 template <int DK> struct ACfg {
     static constexpr int kChunks = DK / 64;                  // 128-byte column chunks per head row
     static constexpr int kSlotBytes = kChunks * KT * 128;    // one plane of a 128-key tile of K (or V)
-    static constexpr int kSmemBytes = kSlots * kSlotBytes + 16 * QT * 4 /*row sums and maxima*/ + 1024 + 256;
+    static constexpr int kSmemBytes = kSlots * kSlotBytes + 16 * QT * 4 /*row sums and maxima*/ + kRedoWords * 4 + 1024 + 256;
     static constexpr uint32_t kTmemCols = 512;
     static constexpr uint32_t kSCol = 0, kOCol = 256, kQCol = 384;
     static constexpr uint32_t kQPlaneCols = DK / 2;          // packed bf16 pairs
@@ -82,6 +90,7 @@ struct AttnParams {
     __nv_bfloat16* ctx_hi;
     __nv_bfloat16* ctx_lo;
     int ldo;
+    int force_exact;                           // FUNASR_B200_ATTENTION_SHIFT=exact: every item in the exact (two-pass) mode
     long long* dbg;                            // tuning aid (FUNASR_B200_ATTN_TIMING): cycles the MMA warp waits, by cause
 };
 
@@ -93,7 +102,8 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t kv_base = (raw + 1023u) & ~1023u;
     const uint32_t l_base = kv_base + kSlots * C::kSlotBytes;              // float[2 item parities][4 groups][128]: row sums, then row maxima
-    const uint32_t bars = l_base + 16 * QT * 4;
+    const uint32_t redo_base = l_base + 16 * QT * 4;                       // uint32[kRedoWords]: items to repeat with the exact shift
+    const uint32_t bars = redo_base + kRedoWords * 4;
     const uint32_t bar_kvfull = bars, bar_kvempty = bars + 8 * kSlots;   // [kSlots] each
     const uint32_t bar_sfull = bars + 16 * kSlots, bar_sempty = bar_sfull + 16;   // [2] each
     const uint32_t bar_pfull = bar_sempty + 16;                          // [2]
@@ -105,11 +115,13 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
     float* l_smem = reinterpret_cast<float*>(smem_raw + (l_base - raw));
     float* mx_smem = l_smem + 8 * QT;
+    volatile uint32_t* redo_bits = reinterpret_cast<volatile uint32_t*>(smem_raw + (redo_base - raw));
 
     const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     const int q_tiles = (p.frames + QT - 1) / QT;
     const int items = p.batch * p.heads * q_tiles;
 
+    if (threadIdx.x < kRedoWords) redo_bits[threadIdx.x] = 0u;
     if (threadIdx.x == 0) {
         for (int s = 0; s < kSlots; ++s) { mbar_init(bar_kvfull + 8 * s, 1); mbar_init(bar_kvempty + 8 * s, 1); }
         for (int s = 0; s < 2; ++s) {
@@ -140,6 +152,24 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
         n = (klen + KT - 1) / KT;
     };
 
+    // A CTA's work is a sequence of (item, mode): first every item of its stride in the fast mode (the shift of a row
+    // is the maximum of its exact scores over the FIRST key tile only; any shift gives the same softmax as long as
+    // nothing overflows, and a row whose sum of weights exceeds 2^60 marks its item), then — after a CTA-wide barrier —
+    // the marked items again in the exact mode (pass 1 over all keys for the shift).  Every role walks the same
+    // sequence, so the barrier phases stay in step.
+    // (written as a pair of macros rather than a lambda taking a lambda: the role bodies keep their state in
+    // registers and are instantiated once)
+#define FA_ATT_SEQUENCE_BEGIN                                                                              \
+    for (int phase = 0; phase < 2; ++phase) {                                                              \
+        if (phase) asm volatile("bar.sync 2, %0;" ::"n"(kAttThreads) : "memory");                          \
+        int k = 0;                                                                                         \
+        for (int item = blockIdx.x; item < items; item += gridDim.x, ++k) {                                \
+            if (phase && !((redo_bits[k >> 5] >> (k & 31)) & 1u)) continue;                                \
+            const bool exact = phase != 0 || p.force_exact != 0;
+#define FA_ATT_SEQUENCE_END \
+        }                   \
+    }
+
     if (warp == 0) {
         // ================================================================== TMA producer
         uint32_t cnt = 0;                             // slots produced so far: slot = cnt % kSlots
@@ -157,11 +187,12 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
             __syncwarp();
             ++cnt;
         };
-        for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        FA_ATT_SEQUENCE_BEGIN
             int b, h, qt, n, klen;
             decode(item, b, h, qt, n, klen);
             const int row0 = b * p.frames;
-            for (int j = 0; j < n; ++j) load_plane(1, 0, h, row0 + j * KT);                    // pass 1: K hi
+            if (exact)
+                for (int j = 0; j < n; ++j) load_plane(1, 0, h, row0 + j * KT);                // pass 1: K hi
             for (int j = 0; j < 2 && j < n; ++j) {                                             // pass 2: K0, K1, then V(j), K(j+2)
                 load_plane(1, 0, h, row0 + j * KT);
                 load_plane(1, 1, h, row0 + j * KT);
@@ -174,7 +205,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
                     load_plane(1, 1, h, row0 + (j + 2) * KT);
                 }
             }
-        }
+        FA_ATT_SEQUENCE_END
     } else if (warp == 1) {
         // ================================================================== MMA issuer
         // The pipe queues only about four instructions ahead of the issuing thread (256 cycles of N = 128 work), so
@@ -219,13 +250,13 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
                 tc_mma_ts(tmem_o, tile + (ks >> 1) * 32 + p_off + (ks & 1) * 8, umma_desc(vpl + ks * 16 * 128, KT * 128, 1024), kIdescO,
                           ks ? 1u : first_accum);
         };
-        for (int item = blockIdx.x; item < items; item += gridDim.x, ++item_it) {
+        FA_ATT_SEQUENCE_BEGIN
             int b, h, qt, n, klen;
             decode(item, b, h, qt, n, klen);
-            twait(0, bar_qfull, item_it & 1);                       // this item's Q is in TMEM
-            // ---- pass 1: shift = max of the hi*hi scores.  Tiles 0, 1 follow the previous item's P V in issue order;
-            // later tiles wait until the softmax group has read the scores they overwrite.
-            for (int j = 0; j < n; ++j) {
+            twait(0, bar_qfull, item_it & 1);                       // this item's Q (hi plane) is in TMEM
+            // ---- pass 1 (exact mode only): shift = max of the hi*hi scores.  Tiles 0, 1 follow the previous item's P V
+            // in issue order; later tiles wait until the softmax group has read the scores they overwrite.
+            for (int j = 0; exact && j < n; ++j) {
                 const uint32_t buf = j & 1;
                 uint32_t s0, p0;
                 take(s0, p0);
@@ -241,8 +272,9 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
                 __syncwarp();
                 toc(12);
             }
-            // ---- pass 2.  S(0), S(1) wait for the last pass-1 scores of their tile to be read; after that S(j+2)
-            // follows P(j) V(j) in issue order and needs no barrier of its own.
+            // ---- pass 2.  S(0), S(1) wait for the last pass-1 scores of their tile to be read (exact mode; in the fast
+            // mode they follow the previous item's P V in issue order); after that S(j+2) follows P(j) V(j) in issue
+            // order and needs no barrier of its own.
             uint32_t ka, kpa, kb, kpb;                              // ring slots of the S about to be issued (K hi, K lo)
             twait(15, bar_qlofull, item_it & 1);                    // the lo plane of Q landed during pass 1
             for (int j = 0; j < 2 && j < n; ++j) {
@@ -250,7 +282,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
                 take(ka, kpa); take(kb, kpb);
                 twait(3, bar_kvfull + 8 * ka, kpa);
                 twait(3, bar_kvfull + 8 * kb, kpb);
-                { uint32_t& se = buf ? se1 : se0; twait(4, bar_sempty + 8 * buf, se & 1); ++se; }
+                if (exact) { uint32_t& se = buf ? se1 : se0; twait(4, bar_sempty + 8 * buf, se & 1); ++se; }
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t tile = tmem_base + C::kSCol + buf * KT;
@@ -328,7 +360,8 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
                     ++pfn;
                 }
             }
-        }
+            ++item_it;
+        FA_ATT_SEQUENCE_END
         if (kAttnTiming && p.dbg && lane == 0) {
             dbg_c[11] = clock64() - dbg_t0;
             for (int i = 0; i < 16; ++i) p.dbg[blockIdx.x * 16 + i] = dbg_c[i];
@@ -343,45 +376,63 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
         const uint32_t tmem_s = tmem_base + lane_addr + C::kSCol + grp * KT + half * 64;
         const uint32_t sfull = bar_sfull + 8 * grp, sempty = bar_sempty + 8 * grp, pfull = bar_pfull + 8 * grp;
         uint32_t item_it = 0, su = 0;
-        for (int item = blockIdx.x; item < items; item += gridDim.x, ++item_it) {
+        // row maximum of this thread's 64 keys of the score tile at tmem_s (keys kbase .. kbase+63, those < klen)
+        auto tile_max = [&](int kbase, int klen, float mx) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t s[32];
+                tc_ld32(tmem_s + c * 32, s);
+                tc_wait_ld();
+                if (kbase + c * 32 + 32 <= klen) {
+                    float m4[4] = {mx, -INFINITY, -INFINITY, -INFINITY};      // four short chains instead of one of 16
+#pragma unroll
+                    for (int i = 0; i < 32; i += 8) {
+#pragma unroll
+                        for (int a = 0; a < 4; ++a)
+                            m4[a] = fmaxf(m4[a], fmaxf(__uint_as_float(s[i + 2 * a]), __uint_as_float(s[i + 2 * a + 1])));
+                    }
+                    mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (kbase + c * 32 + i < klen) mx = fmaxf(mx, __uint_as_float(s[i]));
+                }
+            }
+            return mx;
+        };
+        FA_ATT_SEQUENCE_BEGIN
             int b, h, qt, n, klen;
             decode(item, b, h, qt, n, klen);
             float mx = -INFINITY;
+            float* mxb = mx_smem + (item_it & 1) * 4 * QT;           // buffers alternate by item parity
+            if (!exact) {
+                // ---- fast mode: the shift is the row maximum over key tile 0 (the two groups that own it), taken from
+                // the exact scores pass 2 is about to turn into weights
+                if (grp == 0) {
+                    mbar_wait(sfull, su & 1);                        // S(0); the pass-2 loop waits on it again (at once)
+                    tc_fence_after();
+                    mx = tile_max(half * 64, klen, mx);
+                }
+                mxb[g4 * QT + r] = mx;
+                asm volatile("bar.sync 1, 512;" ::: "memory");
+                mx = fmaxf(mxb[r], mxb[QT + r]);
+            }
             // ---- pass 1 (sharing every tile among all sixteen warps, 32 keys each, was measured and is slower: the
             // fixed cost of a hand-off per tile per warp outweighs the shorter read)
-            for (int j = grp; j < n; j += 2, ++su) {
+            for (int j = grp; exact && j < n; j += 2, ++su) {
                 mbar_wait(sfull, su & 1);
                 tc_fence_after();
-                const int kbase = j * KT + half * 64;
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    uint32_t s[32];
-                    tc_ld32(tmem_s + c * 32, s);
-                    tc_wait_ld();
-                    if (kbase + c * 32 + 32 <= klen) {
-                        float m4[4] = {mx, -INFINITY, -INFINITY, -INFINITY};      // four short chains instead of one of 16
-#pragma unroll
-                        for (int i = 0; i < 32; i += 8) {
-#pragma unroll
-                            for (int a = 0; a < 4; ++a)
-                                m4[a] = fmaxf(m4[a], fmaxf(__uint_as_float(s[i + 2 * a]), __uint_as_float(s[i + 2 * a + 1])));
-                        }
-                        mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (kbase + c * 32 + i < klen) mx = fmaxf(mx, __uint_as_float(s[i]));
-                    }
-                }
+                mx = tile_max(j * KT + half * 64, klen, mx);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(sempty);                 // these scores may be overwritten
             }
-            // the four groups saw disjoint keys: exchange the row maxima (buffers alternate by item parity)
-            float* mxb = mx_smem + (item_it & 1) * 4 * QT;
-            mxb[g4 * QT + r] = mx;
-            asm volatile("bar.sync 1, 512;" ::: "memory");
-            mx = fmaxf(fmaxf(mxb[r], mxb[QT + r]), fmaxf(mxb[2 * QT + r], mxb[3 * QT + r]));
+            if (exact) {
+                // the four groups saw disjoint keys: exchange the row maxima
+                mxb[g4 * QT + r] = mx;
+                asm volatile("bar.sync 1, 512;" ::: "memory");
+                mx = fmaxf(fmaxf(mxb[r], mxb[QT + r]), fmaxf(mxb[2 * QT + r], mxb[3 * QT + r]));
+            }
             // ---- pass 2: scores -> weights in place, 32 keys at a time
             float lsum = 0.f;
             for (int j = grp; j < n; j += 2, ++su) {
@@ -418,7 +469,8 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
             l_smem[((item_it & 1) * 4 + g4) * QT + r] = lsum;
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_lfull + 8 * (item_it & 1));
-        }
+            ++item_it;
+        FA_ATT_SEQUENCE_END
     } else {
         // ================================================================== query loader + output epilogue
         const int quarter = warp & 3;
@@ -459,16 +511,25 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
         };
         uint32_t item_it = 0;
         uint32_t qw[kQW];
-        if ((int)blockIdx.x < items) {
-            q_fetch(blockIdx.x, 0, qw);
+        // this role looks one item ahead, so it walks the two phases of the sequence (see FA_ATT_SEQUENCE_BEGIN) by hand
+        for (int second = 0; second < 2; ++second) {
+            if (second) asm volatile("bar.sync 2, %0;" ::"n"(kAttThreads) : "memory");
+            const bool exact = second || p.force_exact != 0;
+            auto in_phase = [&](int kk) { return !second || (((redo_bits[kk >> 5] >> (kk & 31)) & 1u) != 0u); };
+            auto advance = [&](int& it, int& kk) { do { it += gridDim.x; ++kk; } while (it < items && !in_phase(kk)); };
+            int item = blockIdx.x, k = 0;
+            if (item < items && !in_phase(0)) advance(item, k);
+            if (item >= items) continue;
+            // Q of the phase's first item: nothing is reading Q's columns (kernel start, or every role is past phase 0)
+            q_fetch(item, 0, qw);
             q_store(0, qw, bar_qfull);
-            q_fetch(blockIdx.x, 1, qw);
+            q_fetch(item, 1, qw);
             q_store(1, qw, bar_qlofull);
-        }
-        for (int item = blockIdx.x; item < items; item += gridDim.x, ++item_it) {
+            while (item < items) {
             int b, h, qt, n, klen;
             decode(item, b, h, qt, n, klen);
-            const int next = item + gridDim.x;
+            int next = item, next_k = k;
+            advance(next, next_k);
             if (next < items) {
                 q_fetch(next, 0, qw);                               // in flight while this item's S products finish
                 mbar_wait(bar_qempty, item_it & 1);                 // every S product of this item has retired
@@ -482,40 +543,58 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
             mbar_wait(bar_lfull + 8 * (item_it & 1), (item_it >> 1) & 1);
             tc_fence_after();
             const float* lb = l_smem + (item_it & 1) * 4 * QT + r;
-            const float inv = 1.0f / ((lb[0] + lb[QT]) + (lb[2 * QT] + lb[3 * QT]));
+            const float l_row = (lb[0] + lb[QT]) + (lb[2 * QT] + lb[3 * QT]);
+            const float inv = 1.0f / l_row;
+            // fast mode: a weight above 2^60 means a key outside tile 0 beat the shift by more than 60 (log2 units); the
+            // sums may then have overflowed, so the item is repeated with the exact shift (its output is overwritten)
+            if (!exact && __any_sync(0xffffffffu, !(l_row <= 0x1p60f)) && lane == 0)
+                atomicOr(const_cast<uint32_t*>(redo_bits) + (k >> 5), 1u << (k & 31));
             const int row = qt * QT + r;
             const int64_t grow = (int64_t)b * p.frames + row;
-#pragma unroll 1
-            for (int c = 0; c < DK / 32; ++c) {
-                uint32_t o[32];
-                tc_ld32(tmem_base + lane_addr + C::kOCol + c * 32, o);
-                tc_wait_ld();
-                if (row < p.frames) {
-                    const int64_t off = grow * p.ldo + h * DK + c * 32;
-                    if (p.ctx) {
+            // O leaves TMEM 64 columns at a time; the accumulator is handed back to the MMA warp as soon as the last
+            // columns are in registers, before they are scaled, split and stored (the next item's first P V is only
+            // some three thousand cycles behind this item's last one)
+            auto emit = [&](const uint32_t (&o)[32], int c) {
+                if (row >= p.frames) return;
+                const int64_t off = grow * p.ldo + h * DK + c * 32;
+                if (p.ctx) {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            *reinterpret_cast<float4*>(p.ctx + off + 4 * i) =
-                                make_float4(__uint_as_float(o[4 * i]) * inv, __uint_as_float(o[4 * i + 1]) * inv,
-                                            __uint_as_float(o[4 * i + 2]) * inv, __uint_as_float(o[4 * i + 3]) * inv);
-                    }
-                    if (p.ctx_hi) {
-                        uint32_t hw[16], lw[16];
+                    for (int i = 0; i < 8; ++i)
+                        *reinterpret_cast<float4*>(p.ctx + off + 4 * i) =
+                            make_float4(__uint_as_float(o[4 * i]) * inv, __uint_as_float(o[4 * i + 1]) * inv,
+                                        __uint_as_float(o[4 * i + 2]) * inv, __uint_as_float(o[4 * i + 3]) * inv);
+                }
+                if (p.ctx_hi) {
+                    uint32_t hw[16], lw[16];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                            split_bf16x2(__uint_as_float(o[2 * i]) * inv, __uint_as_float(o[2 * i + 1]) * inv, hw[i], lw[i]);
+                    for (int i = 0; i < 16; ++i)
+                        split_bf16x2(__uint_as_float(o[2 * i]) * inv, __uint_as_float(o[2 * i + 1]) * inv, hw[i], lw[i]);
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            reinterpret_cast<uint4*>(p.ctx_hi + off)[i] = make_uint4(hw[4 * i], hw[4 * i + 1], hw[4 * i + 2], hw[4 * i + 3]);
-                            if (p.ctx_lo)
-                                reinterpret_cast<uint4*>(p.ctx_lo + off)[i] = make_uint4(lw[4 * i], lw[4 * i + 1], lw[4 * i + 2], lw[4 * i + 3]);
-                        }
+                    for (int i = 0; i < 4; ++i) {
+                        reinterpret_cast<uint4*>(p.ctx_hi + off)[i] = make_uint4(hw[4 * i], hw[4 * i + 1], hw[4 * i + 2], hw[4 * i + 3]);
+                        if (p.ctx_lo)
+                            reinterpret_cast<uint4*>(p.ctx_lo + off)[i] = make_uint4(lw[4 * i], lw[4 * i + 1], lw[4 * i + 2], lw[4 * i + 3]);
                     }
                 }
+            };
+#pragma unroll 1
+            for (int c = 0; c < DK / 32; c += 2) {
+                uint32_t o0[32], o1[32];
+                tc_ld32(tmem_base + lane_addr + C::kOCol + c * 32, o0);
+                tc_ld32(tmem_base + lane_addr + C::kOCol + c * 32 + 32, o1);
+                tc_wait_ld();
+                if (c + 2 == DK / 32) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_oempty);
+                }
+                emit(o0, c);
+                emit(o1, c + 1);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_oempty);
+            ++item_it;
+            item = next;
+            k = next_k;
+            }
         }
     }
 
@@ -526,6 +605,9 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
         tmem_dealloc(tmem_base, C::kTmemCols);
     }
 }
+
+#undef FA_ATT_SEQUENCE_BEGIN
+#undef FA_ATT_SEQUENCE_END
 
 int g_att_sms = 0;
 
@@ -551,6 +633,10 @@ void launch_attention_tc(Planes qkv, int64_t plane_stride, int ld, int d_model, 
     p.batch = batch; p.frames = frames; p.heads = heads; p.d_model = d_model; p.ld = ld; p.kv_len = kv_len;
     p.q_hi = qkv.hi; p.q_lo = qkv.lo;
     p.ctx = ctx_f32; p.ctx_hi = ctx_pl.hi; p.ctx_lo = ctx_pl.lo; p.ldo = ldo;
+    {
+        const char* sh = getenv("FUNASR_B200_ATTENTION_SHIFT");      // comparison aid, read at every launch
+        p.force_exact = (sh && !strcmp(sh, "exact")) ? 1 : 0;
+    }
     const int items = batch * heads * cdiv(frames, QT);
     const int grid = items < g_att_sms ? items : g_att_sms;
     static const bool timing = kAttnTiming && getenv("FUNASR_B200_ATTN_TIMING") != nullptr;

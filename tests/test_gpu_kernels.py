@@ -231,6 +231,35 @@ def test_attention_peaked_scores(raw):
         assert rel_err(raw.attention(qkv, b, t, heads, dk, None, precision=precision), ref) <= 10 * ATT_TOL[precision]
 
 
+@pytest.mark.parametrize("heads,dk", [(4, 128), (8, 64)])
+def test_attention_outlier_key_beyond_the_first_tile_repeats_the_item_exactly(raw, heads, dk):
+    """The tensor-core kernel takes a row's shift from key tile 0 only and repeats an item with the exact two-pass shift
+    when a later key beats that shift by more than 2^60 in weight.  Segment 0: no outlier (fast mode only).  Segment 1:
+    key 300 scores ~100 (log2 units) above everything for every query, far past fp32 exp2 range without the exact
+    shift.  Segment 2: the same outlier inside tile 0 (fast mode copes: it IS the shift).  Segment 3: outlier at key 700
+    but masked out by kv_len."""
+    b, t, d = 4, 900, heads * dk
+    qkv = _rand((b * t, 3 * d), 51, 0.7)
+    x = qkv.reshape(b, t, 3, heads, dk)
+    u = _rand((dk,), 52)
+    u /= np.linalg.norm(u)
+    x[1:, :, 0] += 8.0 * u                                   # every query of segments 1..3 leans along u
+    for seg, key in ((1, 300), (2, 17), (3, 700)):
+        x[seg, key, 1] = 110.0 * u                           # ... and one key is huge along u
+    qkv = np.ascontiguousarray(x.reshape(b * t, 3 * d))
+    kv_len = [t, t, t, 650]
+    xt = torch.from_numpy(qkv).double().view(b, t, 3, heads, dk)
+    q, k, v = (xt[:, :, i].transpose(1, 2) for i in range(3))
+    s = (q * dk ** -0.5) @ k.transpose(-2, -1)
+    assert float((s[1, :, :, 300] - s[1, :, :, :128].amax(-1)).min()) * 1.4427 > 70.0     # the redo really triggers
+    mask = (torch.arange(t).view(1, 1, 1, t) < torch.tensor(kv_len).view(b, 1, 1, 1)).double()
+    ref = (torch.softmax(s + (mask - 1.0) * 10000.0, -1) @ v).transpose(1, 2).reshape(b * t, d)
+    for precision in ("fp32", "bf16x3"):
+        got = raw.attention(qkv, b, t, heads, dk, kv_len, precision=precision)
+        assert np.isfinite(got).all()
+        assert rel_err(got, ref) <= 10 * ATT_TOL[precision]
+
+
 @pytest.mark.parametrize("d,eps", [(512, 1e-5), (560, 1e-5), (1024, 1e-12), (512, 1e-12)])
 def test_layernorm(raw, d, eps):
     x = _rand((333, d), 14, 3.0) + 0.5
