@@ -245,6 +245,66 @@ def test_lookahead_long_file_matches_per_segment_calls(weights):
     engine.close()
 
 
+def test_config4_full_size_one_hour_file(planted_weights):
+    """BASELINE config 4 at full size: 3600 s of audio cut exactly as core/orchestrator.py:128-136 cuts it
+    (60 s windows, 4 s overlap): 65 windows, 64 x 60 s + 1 x 16 s.  The look-ahead path batches the equal-length windows
+    (32 per batch: the candidate-list vocabulary path, CTA-pair GEMMs); a sample of windows, including the first, the
+    last full one and the short tail, must equal the single-window calls of the reference's loop: ids identical,
+    activations to within the re-association noise of a different batch shape."""
+    from fun_asr_gguf_b200 import lookahead, segments
+    sr = 16000
+    n = 3600 * sr
+    rng = np.random.default_rng(4)
+    audio = np.concatenate([signals.structured(60 * sr, 200 + i).numpy() * float(rng.uniform(0.3, 1.0)) for i in range(60)])
+    assert audio.shape[0] == n
+    windows = segments.segment_windows(n)
+    assert len(windows) == 65 and windows[1][0] == 56 * sr and windows[-1] == (3584 * sr, n)
+    assert sum(1 for a, b in windows if b - a == 60 * sr) == 64 and windows[-1][1] - windows[-1][0] == 16 * sr
+    engine = FrontHalf(planted_weights, device=0, max_batch=32, max_samples=60 * sr, precision="bf16x3")
+    try:
+        res = lookahead.run_file(engine, audio)
+        assert len(res) == 65 and all(r is not None for r in res)
+        for k in (0, 1, 31, 32, 63, 64):
+            a, b = windows[k]
+            enc, ad, ids = engine.front_half(audio[None, a:b], [b - a])
+            r = res[k]
+            # a single window takes the three-product vocabulary projection, a batch of 32 the candidate lists with
+            # fp32 rescoring: the ids may differ on a near-tie (both are inside the parity contract)
+            assert (ids != r.ids).sum() <= 2
+            assert np.abs(enc - r.enc_output).max() <= 1e-5 * max(np.abs(enc).max(), 1.0)
+            assert np.abs(ad - r.adaptor_output).max() <= 1e-5 * max(np.abs(ad).max(), 1.0)
+            assert len(np.unique(r.ids)) > 20                       # the planted projection makes the ids vary
+        # neighbouring windows overlap by 4 s of audio but are independent computations: nothing is shared or reused
+        assert not np.array_equal(res[0].ids, res[1].ids)
+    finally:
+        engine.close()
+
+
+def test_config5_full_size_256_segments_in_batches(weights):
+    """BASELINE config 5 at full size: 256 x 60 s segments through a context of 32 (8 internal batches).
+    The 256 segments are 32 distinct signals repeated 8 times, so every repeat must reproduce the first batch bit for
+    bit (a batch's result may not depend on what ran before it, nor on its position in the call), and the launch
+    counter must grow by 8 steps' worth."""
+    sr = 16000
+    s = 60 * sr
+    base = np.stack([signals.white(s, 300 + i).numpy() for i in range(32)])
+    engine = FrontHalf(weights, device=0, max_batch=32, max_samples=s, precision="bf16x3")
+    try:
+        n0 = engine.launch_count()
+        enc1, ad1, ids1 = engine.front_half(base, [s] * 32)
+        per_step = engine.launch_count() - n0
+        big = np.concatenate([base] * 8)
+        n0 = engine.launch_count()
+        enc, ad, ids = engine.front_half(big, [s] * 256, want_adaptor=False)
+        assert engine.launch_count() - n0 == 8 * per_step
+        assert enc.shape == (256, 1001, 512) and ids.shape == (256, 1001)
+        for rep in range(8):
+            assert np.array_equal(ids[32 * rep:32 * rep + 32], ids1)
+            assert np.array_equal(enc[32 * rep:32 * rep + 32], enc1)
+    finally:
+        engine.close()
+
+
 def test_config3_full_size_mixed_length_batch(weights, planted_weights, consts):
     """BASELINE config 3 at full size: 32 items, lengths randint(80 000, 960 001) from seed 1234, each
     zero-padded to the batch maximum.  Every row must be bit-identical to the same row run alone at the same physical
