@@ -114,6 +114,11 @@ Context::Context(int device, int max_batch, int64_t max_samples, int precision)
     const char* att = getenv("FUNASR_B200_ATTENTION");     // debugging aid: "simt" keeps fp32 attention in the tensor-core modes
     simt_attention_ = precision == kFp32 || (att && std::string(att) == "simt");
     if (const char* g = getenv("FUNASR_B200_GRAPH_MAX_BATCH")) graph_max_batch_ = std::max(0, atoi(g));
+    {
+        const char* g = getenv("FUNASR_B200_FBANK");          // comparison aid
+        fbank_tc_ = precision != kFp32 && !(g && std::string(g) == "simt");
+        if (fbank_tc_) fbank_tc_init_device();
+    }
     t_mel_max_ = (int)(max_samples / kHop + 1);
     t_max_ = lfr_frames_of(max_samples);
     m_max_ = (int64_t)max_batch * t_max_;
@@ -313,6 +318,12 @@ void Context::finalize() {
         derived_.back()->alloc(range.size() * sizeof(int));
         FA_CUDA(cudaMemcpy(derived_.back()->p, range.data(), range.size() * sizeof(int), cudaMemcpyHostToDevice));
         mel_range_ = derived_.back()->as<int>();
+        if (fbank_tc_) {
+            derived_.emplace_back(new DevBuf);
+            derived_.back()->alloc(fbank_tc_table_bytes());
+            dft_planes_ = derived_.back()->p;
+            launch_fbank_table_planes(dft_t_, dft_planes_, stream_);
+        }
         auto it = tensors_.find("const.pos_enc");
         if (it == tensors_.end() || it->second.shape.size() != 2 || it->second.shape[1] != kDin)
             throw Error("missing or malformed tensor: const.pos_enc");
@@ -327,6 +338,10 @@ void Context::finalize() {
     audio_.alloc((size_t)max_batch_ * max_samples_ * 4);
     partials_.alloc((size_t)max_batch_ * kMeanParts * 8);
     logmel_.alloc((size_t)max_batch_ * t_mel_max_ * kMels * 4);
+    if (fbank_tc_) {
+        yplanes_.alloc((size_t)2 * max_batch_ * fbank_tc_padded_samples(max_samples_) * 2);
+        power_.alloc((size_t)max_batch_ * t_mel_max_ * fbank_tc_power_ld() * 4);
+    }
     x0_.alloc(M * kDin * 4);
     x_.alloc(M * kDllm * 4);
     qkv_.alloc(M * 3 * kDllm * 4);
@@ -552,8 +567,13 @@ void Context::front_end(const float* d_audio, int b0, int nb, int64_t s_phys) {
     const int t_mel = (int)(s_phys / kHop + 1);
     double* parts = partials_.as<double>() + (size_t)b0 * kMeanParts;
     launch_segment_sums(d_audio, nb, s_phys, d_nvalid_ + b0, parts, stream_);
-    launch_fbank(d_audio, nb, s_phys, d_nvalid_ + b0, parts, dft_t_, melfb_t_, mel_range_,
-                 logmel_.as<float>() + (size_t)b0 * t_mel * kMels, t_mel, stream_);
+    if (fbank_tc_) {
+        launch_fbank_tc(d_audio, nb, s_phys, d_nvalid_ + b0, parts, dft_planes_, melfb_t_, mel_range_, yplanes_.p,
+                        power_.as<float>(), logmel_.as<float>() + (size_t)b0 * t_mel * kMels, t_mel, stream_);
+    } else {
+        launch_fbank(d_audio, nb, s_phys, d_nvalid_ + b0, parts, dft_t_, melfb_t_, mel_range_,
+                     logmel_.as<float>() + (size_t)b0 * t_mel * kMels, t_mel, stream_);
+    }
 }
 
 void Context::encode_dev(const float* d_audio, int batch, int64_t s_phys, const int64_t* h_ilens, float* d_enc,

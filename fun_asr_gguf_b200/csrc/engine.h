@@ -156,7 +156,7 @@ private:
 
     // workspace
     DevBuf audio_, partials_, logmel_, x0_, x_, h32_, hpl_, qkv_, qkvpl_, ctx32_, ctxpl_, ffn32_, ffnpl_, encpl_, enc_,
-        adaptor_out_, ids_, amax_val_, amax_idx_, logits_, lens_, tokens_, cand_meta_, cand_list_;
+        adaptor_out_, ids_, amax_val_, amax_idx_, logits_, lens_, tokens_, cand_meta_, cand_list_, yplanes_, power_;
     float vocab_wnorm_ = 0.f;                 // max_c |w_c|_2 of ctc_lo (bound of the one-product vocabulary pass)
     bool vocab_rescore_ = false;              // bf16x3: one-product pass + exact rescoring of the candidates
     int* d_nvalid_ = nullptr;
@@ -166,6 +166,8 @@ private:
     int logits_rows_ = 0;
     struct GraphEntry { cudaGraphExec_t exec = nullptr; int64_t launches = 0; };
     std::map<std::tuple<int, int, int64_t>, GraphEntry> graphs_;
+    bool fbank_tc_ = true;                    // DFT of the front end on the tensor cores (FUNASR_B200_FBANK=simt: CUDA cores)
+    void* dft_planes_ = nullptr;              // fp16 hi/lo planes of the DFT table (tensor-core front end)
     int graph_max_batch_ = 4;                 // FUNASR_B200_GRAPH_MAX_BATCH (0 turns graph replay off)
     std::map<std::string, std::pair<std::vector<int64_t>, std::unique_ptr<DevBuf>>> taps_;
 };

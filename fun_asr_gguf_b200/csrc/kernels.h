@@ -22,6 +22,17 @@ void launch_fbank(const float* audio, int batch, int64_t s_phys, const int* n_va
                   const float* dft_t /*[400][kDftLd] cos|sin transposed*/, const float* melfb /*[201][80] transposed*/,
                   const int* mel_range /*[80][2] first / last+1 non-zero bin of each filter*/,
                   float* logmel, int t_mel, cudaStream_t st);
+// The same front end with the DFT on the tensor cores (fbank_tc.cu): fp16 hi/lo planes, three products, fp32 TMEM
+// accumulators; y_planes holds 2 * batch * fbank_tc_padded_samples(s_phys) halves, power batch * t_mel * fbank_tc_power_ld()
+// floats, table_planes fbank_tc_table_bytes() bytes filled once by launch_fbank_table_planes.
+void fbank_tc_init_device();
+int64_t fbank_tc_padded_samples(int64_t s_phys);
+size_t fbank_tc_table_bytes();
+int fbank_tc_power_ld();
+void launch_fbank_table_planes(const float* dft_t, void* table_planes, cudaStream_t st);
+void launch_fbank_tc(const float* audio, int batch, int64_t s_phys, const int* n_valid, const double* partials,
+                     const void* table_planes, const float* melfb_t, const int* mel_range, void* y_planes, float* power,
+                     float* logmel, int t_mel, cudaStream_t st);
 constexpr int kDftLd = 416;   // 402 real columns (201 cos + 201 -sin), padded
 // LFR stacking with replicate padding, frame mask, sqrt(512) scale and positional table.
 void launch_lfr_embed(const float* logmel, int batch, int t_mel, int t_lfr, const int* n_valid, const float* pos_enc,
