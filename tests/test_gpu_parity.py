@@ -83,6 +83,44 @@ def test_front_end_taps(engine, weights, consts):
         assert np.abs(engine.read_tap(name) - taps[name].numpy()).max() <= tol, name
 
 
+@pytest.mark.parametrize("kind", ["structured", "tone", "white", "quiet", "loud"])
+def test_tensor_core_front_end_matches_oracle_and_cuda_core_front_end(weights, consts, monkeypatch, kind):
+    """The DFT runs on the tensor cores from fp16 hi/lo planes (fbank_tc.cu); FUNASR_B200_FBANK=simt keeps the fp32
+    CUDA-core kernel.  Both must meet the same log-mel tolerance against the oracle, on signals that stress what a
+    split-precision product could get wrong: a tone 70 dB above the noise floor (weak bins next to a strong one), a
+    signal at 1e-4 of full scale (lo planes near fp16's subnormal range), one at full scale, white noise, speech-like."""
+    s, n_valid = 4 * SR, 4 * SR - 777
+    t = torch.arange(s, dtype=torch.float64) / SR
+    if kind == "structured":
+        x = signals.structured(s, 71)
+    elif kind == "tone":
+        x = (0.5 * torch.sin(2 * np.pi * 1000.0 * t)).float() + 1e-4 * signals.white(s, 72)
+    elif kind == "white":
+        x = signals.white(s, 73)
+    elif kind == "quiet":
+        x = 1e-3 * signals.white(s, 74)
+    else:
+        x = (0.99 * torch.sign(torch.sin(2 * np.pi * 313.0 * t))).float()
+    audio = signals.padded(x[:n_valid], s)
+    taps = {}
+    O.encode_one(audio, n_valid, weights, consts, taps=taps)
+    ref = taps["logmel"].numpy()
+    got = {}
+    for mode in ("tc", "simt"):
+        if mode == "simt":
+            monkeypatch.setenv("FUNASR_B200_FBANK", "simt")
+        eng = FrontHalf(weights, device=0, max_batch=1, max_samples=s, precision="bf16x3")
+        try:
+            eng.enable_taps(True)
+            eng.front_half(audio.numpy()[None], [n_valid])
+            got[mode] = eng.read_tap("logmel")
+        finally:
+            eng.close()
+        assert np.abs(np.exp(got[mode]) - np.exp(ref)).max() <= 1e-5 * max(1.0, float(np.exp(ref).max())), mode
+        assert np.abs(got[mode] - ref).max() <= 5e-3, mode
+    assert np.abs(got["tc"] - got["simt"]).max() <= 5e-3
+
+
 def test_mixed_length_batch_rows_are_independent(engine, weights, consts):
     """BASELINE config 3 in miniature: ragged lengths padded to the batch max; each row equals a
     batch-1 oracle run at the same physical length."""
