@@ -29,6 +29,7 @@ void prof_note_work(double flops, double bytes) { g_next_flops = flops; g_next_b
 void prof_before(const char* kernel, cudaStream_t st) {
     ProfRec r;
     r.name = kernel;
+    if (!r.name.empty() && r.name[0] == '(') r.name.erase(0, 1);      // FA_LAUNCH((k<a, b>), ...) stringifies with its parentheses
     const size_t lt = r.name.find('<');
     if (lt != std::string::npos && r.name.find("k_gemm_tc") == std::string::npos) r.name = r.name.substr(0, lt);
     r.flops = g_next_flops; r.bytes = g_next_bytes;
