@@ -62,7 +62,8 @@ constexpr int KT = 128;          // keys per tile (UMMA N for S, K extent for PV
 constexpr int kAttThreads = 704;
 constexpr int kSlots = 6;
 constexpr int kRedoWords = 64;       // one bit per item of a CTA's sequence (2048 items per CTA)
-constexpr bool kAttnTiming = false;   // tuning aid: set true, rebuild, run with FUNASR_B200_ATTN_TIMING=1 (per-cause wait cycles of the MMA warp)
+constexpr bool kAttnTiming = false;
+constexpr bool kAttnTrace = false;    // tuning aid: clock64 stamps of CTA 0's roles per item (set true, rebuild, FUNASR_B200_ATTN_TIMING=1)   // tuning aid: set true, rebuild, run with FUNASR_B200_ATTN_TIMING=1 (per-cause wait cycles of the MMA warp)
 
 template <int DK> struct ACfg {
     static constexpr int kChunks = DK / 64;                  // 128-byte column chunks per head row
@@ -159,6 +160,13 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
     // sequence, so the barrier phases stay in step.
     // (written as a pair of macros rather than a lambda taking a lambda: the role bodies keep their state in
     // registers and are instantiated once)
+    auto trace = [&](uint32_t it, int ev) {
+        if (kAttnTrace && p.dbg && blockIdx.x == 0 && lane == 0 && it < 8) {
+            long long t;
+            asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory");
+            p.dbg[it * 32 + ev] = t;
+        }
+    };
 #define FA_ATT_SEQUENCE_BEGIN                                                                              \
     for (int phase = 0; phase < 2; ++phase) {                                                              \
         if (phase) asm volatile("bar.sync 2, %0;" ::"n"(kAttThreads) : "memory");                          \
@@ -253,7 +261,9 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
         FA_ATT_SEQUENCE_BEGIN
             int b, h, qt, n, klen;
             decode(item, b, h, qt, n, klen);
-            twait(0, bar_qfull, item_it & 1);                       // this item's Q (hi plane) is in TMEM
+            trace(item_it, 0);
+            twait(0, bar_qfull, item_it & 1);
+            trace(item_it, 1);                       // this item's Q (hi plane) is in TMEM
             // ---- pass 1 (exact mode only): shift = max of the hi*hi scores.  Tiles 0, 1 follow the previous item's P V
             // in issue order; later tiles wait until the softmax group has read the scores they overwrite.
             for (int j = 0; exact && j < n; ++j) {
@@ -277,6 +287,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
             // order and needs no barrier of its own.
             uint32_t ka, kpa, kb, kpb;                              // ring slots of the S about to be issued (K hi, K lo)
             twait(15, bar_qlofull, item_it & 1);                    // the lo plane of Q landed during pass 1
+            trace(item_it, 2);
             for (int j = 0; j < 2 && j < n; ++j) {
                 const uint32_t buf = j;
                 take(ka, kpa); take(kb, kpb);
@@ -299,10 +310,14 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
             // barriers of P(0) V(0): V hi, V lo, the weights, a drained O
             uint32_t va, vpa, vb, vpb;
             take(va, vpa); take(vb, vpb);
+            trace(item_it, 3);
             twait(5, bar_oempty, (item_it & 1) ^ 1);
+            trace(item_it, 4);
             twait(6, bar_kvfull + 8 * va, vpa);
             twait(6, bar_kvfull + 8 * vb, vpb);
+            trace(item_it, 5);
             twait(7, bar_pfull, pf0 & 1);
+            trace(item_it, 6);
             ++pf0;
             for (int j = 0; j < n; ++j) {
                 const uint32_t buf = j & 1;
@@ -360,6 +375,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
                     ++pfn;
                 }
             }
+            trace(item_it, 7);
             ++item_it;
         FA_ATT_SEQUENCE_END
         if (kAttnTiming && p.dbg && lane == 0) {
@@ -405,17 +421,21 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
             decode(item, b, h, qt, n, klen);
             float mx = -INFINITY;
             float* mxb = mx_smem + (item_it & 1) * 4 * QT;           // buffers alternate by item parity
+            if (warp == 2) trace(item_it, 16);
             if (!exact) {
                 // ---- fast mode: the shift is the row maximum over key tile 0 (the two groups that own it), taken from
                 // the exact scores pass 2 is about to turn into weights
                 if (grp == 0) {
                     mbar_wait(sfull, su & 1);                        // S(0); the pass-2 loop waits on it again (at once)
+                    if (warp == 2) trace(item_it, 17);
                     tc_fence_after();
                     mx = tile_max(half * 64, klen, mx);
+                    if (warp == 2) trace(item_it, 18);
                 }
                 mxb[g4 * QT + r] = mx;
                 asm volatile("bar.sync 1, 512;" ::: "memory");
                 mx = fmaxf(mxb[r], mxb[QT + r]);
+                if (warp == 2) trace(item_it, 19);
             }
             // ---- pass 1 (sharing every tile among all sixteen warps, 32 keys each, was measured and is slower: the
             // fixed cost of a hand-off per tile per warp outweighs the shorter read)
@@ -464,6 +484,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(pfull);
+                if (warp == 2 && j < 2) trace(item_it, 20);
             }
             // ---- hand this group's row sums to the epilogue warps
             l_smem[((item_it & 1) * 4 + g4) * QT + r] = lsum;
@@ -533,13 +554,17 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
             if (next < items) {
                 q_fetch(next, 0, qw);                               // in flight while this item's S products finish
                 mbar_wait(bar_qempty, item_it & 1);                 // every S product of this item has retired
+                if (warp == 18) trace(item_it, 8);
                 tc_fence_after();
                 q_store(0, qw, bar_qfull);
+                if (warp == 18) trace(item_it, 9);
                 q_fetch(next, 1, qw);
                 q_store(1, qw, bar_qlofull);
+                if (warp == 18) trace(item_it, 10);
             }
             // ---- epilogue: O / l
             mbar_wait(bar_ofull, item_it & 1);
+            if (warp == 18) trace(item_it, 11);
             mbar_wait(bar_lfull + 8 * (item_it & 1), (item_it >> 1) & 1);
             tc_fence_after();
             const float* lb = l_smem + (item_it & 1) * 4 * QT + r;
@@ -587,10 +612,12 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_oempty);
+                    if (warp == 18) trace(item_it, 13);
                 }
                 emit(o0, c);
                 emit(o1, c + 1);
             }
+            if (warp == 18) trace(item_it, 14);
             ++item_it;
             item = next;
             k = next_k;
@@ -638,10 +665,15 @@ void launch_attention_tc(Planes qkv, int64_t plane_stride, int ld, int d_model, 
         p.force_exact = (sh && !strcmp(sh, "exact")) ? 1 : 0;
     }
     const int items = batch * heads * cdiv(frames, QT);
-    const int grid = items < g_att_sms ? items : g_att_sms;
-    static const bool timing = kAttnTiming && getenv("FUNASR_B200_ATTN_TIMING") != nullptr;
+    int grid = items < g_att_sms ? items : g_att_sms;
+    if (const char* e = getenv("FUNASR_B200_ATT_SMS")) { const int v = atoi(e); if (v > 0 && v < grid) grid = v; }   // tuning aid: fewer CTAs
+    static const bool timing = (kAttnTiming || kAttnTrace) && getenv("FUNASR_B200_ATTN_TIMING") != nullptr;
     long long* dbg = nullptr;
-    if (timing) { FA_CUDA(cudaMalloc(&dbg, (size_t)grid * 16 * sizeof(long long))); p.dbg = dbg; }
+    if (timing) {
+        FA_CUDA(cudaMalloc(&dbg, (size_t)grid * 16 * sizeof(long long)));
+        FA_CUDA(cudaMemsetAsync(dbg, 0, (size_t)grid * 16 * sizeof(long long), st));
+        p.dbg = dbg;
+    }
     prof_note_work(4.0 * batch * heads * (double)frames * frames * dk, 0.0);
     if (dk == 128) {
         FA_LAUNCH(k_attention_tc<128>, grid, kAttThreads, ACfg<128>::kSmemBytes, st, mkv.map, p);
@@ -653,6 +685,16 @@ void launch_attention_tc(Planes qkv, int64_t plane_stride, int ld, int d_model, 
         FA_CUDA(cudaStreamSynchronize(st));
         FA_CUDA(cudaMemcpy(h.data(), dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
         FA_CUDA(cudaFree(dbg));
+        if (kAttnTrace) {   // events: MMA warp 0 item start, 1 Q hi, 2 Q lo, 3 S(0) S(1) issued, 4 O drained, 5 first V, 6 first P, 7 item issued;
+                            // loader 8 Q free, 9/10 next Q hi/lo stored, 11 O complete, 13 O handed back, 14 output stored;
+                            // softmax warp 2: 16 item start, 17 S(0) seen, 18 tile maximum, 19 shift exchanged, 20 P(0) written
+            for (int it = 0; it < 8; ++it) {
+                fprintf(stderr, "trace item %d:", it);
+                for (int e = 0; e < 32; ++e) fprintf(stderr, " %d=%lld", e, h[it * 32 + e] ? h[it * 32 + e] - h[0] : -1LL);
+                fprintf(stderr, "\n");
+            }
+            return;
+        }
         double c[16] = {0};
         for (int b = 0; b < grid; ++b)
             for (int i = 0; i < 16; ++i) c[i] += (double)h[(size_t)b * 16 + i] / grid;

@@ -944,6 +944,25 @@ void Context::test_attention(const float* qkv, int batch, int frames, int heads,
         dpl.alloc(M * 3 * d * 2 * 2);
         Planes pl{dpl.as<__nv_bfloat16>(), dpl.as<__nv_bfloat16>() + M * 3 * d};
         launch_split_planes(dq.as<float>(), (int64_t)(M * 3 * d), pl, stream_);
+        // FUNASR_B200_TEST_ATTN_OUT=planes: write the bf16 hi/lo planes the out-projection reads (what every engine launch
+        // does) instead of fp32, and hand back hi + lo
+        const char* om = getenv("FUNASR_B200_TEST_ATTN_OUT");
+        if (om && !strcmp(om, "planes")) {
+            DevBuf dop;
+            dop.alloc(M * d * 2 * 2);
+            Planes op{dop.as<__nv_bfloat16>(), dop.as<__nv_bfloat16>() + M * d};
+            launch_attention_tc(pl, (int64_t)(M * 3 * d), 3 * d, d, batch, frames, heads, dk, dl.as<int>(), nullptr, op, d, stream_);
+            FA_CUDA(cudaStreamSynchronize(stream_));
+            std::vector<uint16_t> h(M * d * 2);
+            FA_CUDA(cudaMemcpy(h.data(), dop.p, dop.bytes, cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < M * d; ++i) {
+                const uint32_t hb = (uint32_t)h[i] << 16, lb = (uint32_t)h[M * d + i] << 16;
+                float hf, lf;
+                memcpy(&hf, &hb, 4); memcpy(&lf, &lb, 4);
+                out[i] = hf + lf;
+            }
+            return;
+        }
         launch_attention_tc(pl, (int64_t)(M * 3 * d), 3 * d, d, batch, frames, heads, dk, dl.as<int>(), dout.as<float>(),
                             Planes{}, d, stream_);
     }

@@ -200,9 +200,17 @@ def test_vocab_argmax_ties_pick_first_index(raw, vocab_mode):
 ATT_TOL = {"fp32": 5e-6, "bf16x3": 4e-5}
 
 
+@pytest.fixture(params=["f32", "planes"])
+def att_out(request, monkeypatch):
+    """Output form of the tensor-core attention kernel under test: fp32 rows, or the bf16 hi/lo planes every engine
+    launch writes for the out-projection (handed back as hi + lo)."""
+    monkeypatch.setenv("FUNASR_B200_TEST_ATTN_OUT", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
 @pytest.mark.parametrize("heads,dk,t", [(4, 128, 150), (8, 128, 150), (8, 64, 150), (4, 128, 1001), (8, 64, 333)])
-def test_attention_masked_keys(raw, precision, heads, dk, t):
+def test_attention_masked_keys(raw, att_out, precision, heads, dk, t):
     b, d = 3, heads * dk
     qkv = _rand((b * t, 3 * d), 13, 0.7)
     kv_len = [t, (t * 2) // 3 + 1, 1]
@@ -219,7 +227,7 @@ def test_attention_masked_keys(raw, precision, heads, dk, t):
     assert rel_err(got_full, ref_full) <= ATT_TOL[precision]
 
 
-def test_attention_peaked_scores(raw):
+def test_attention_peaked_scores(raw, att_out):
     """Large |scores| (sharp softmax): the two-pass max must keep exp2 in range on the tensor-core path."""
     b, t, heads, dk = 2, 200, 4, 128
     qkv = _rand((b * t, 3 * heads * dk), 21, 1.0)
@@ -232,7 +240,7 @@ def test_attention_peaked_scores(raw):
 
 
 @pytest.mark.parametrize("heads,dk", [(4, 128), (8, 64)])
-def test_attention_outlier_key_beyond_the_first_tile_repeats_the_item_exactly(raw, heads, dk):
+def test_attention_outlier_key_beyond_the_first_tile_repeats_the_item_exactly(raw, att_out, heads, dk):
     """The tensor-core kernel takes a row's shift from key tile 0 only and repeats an item with the exact two-pass shift
     when a later key beats that shift by more than 2^60 in weight.  Segment 0: no outlier (fast mode only).  Segment 1:
     key 300 scores ~100 (log2 units) above everything for every query, far past fp32 exp2 range without the exact

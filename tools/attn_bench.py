@@ -6,6 +6,7 @@ Short isolated launches run at whatever clock the idle GPU ramps to: compare run
 not with the per-kernel times of a full step.
 """
 import os, sys
+os.environ.setdefault("FUNASR_B200_TEST_ATTN_OUT", "planes")   # what the engine's launches write
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np
