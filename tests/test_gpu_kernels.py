@@ -289,3 +289,21 @@ def test_fsmn_memory_block(raw):
     ref = conv + vm
     assert rel_err(raw.fsmn(v, w, tv), ref) <= 2e-6
     assert rel_err(raw.fsmn(v, w, tv, resid), ref + torch.from_numpy(resid).double()) <= 2e-6
+
+
+def test_fsmn_streaming_kernel_matches_the_strip_kernel_bit_for_bit(raw, monkeypatch):
+    """The persistent double-buffered kernel (bulk copies into shared memory, FUNASR_B200_FSMN=stream) against the
+    register-strip kernel, on enough strips that every CTA walks several of them: full, ragged, one-frame and empty-tail segments."""
+    b, t = 40, 333
+    v, w = _rand((b, t, 512), 27), _rand((512, 11), 28, 0.3)
+    resid = _rand((b, t, 512), 29)
+    tv = [t, 1, 5, 16, 17, 100, 332, 11] * 5
+    got = raw.fsmn(v, w, tv, resid)
+    got0 = raw.fsmn(v, w, tv)
+    monkeypatch.setenv("FUNASR_B200_FSMN", "stream")
+    assert np.array_equal(got, raw.fsmn(v, w, tv, resid))
+    assert np.array_equal(got0, raw.fsmn(v, w, tv))
+    m = (torch.arange(t).view(1, t, 1) < torch.tensor(tv).view(b, 1, 1)).double()
+    vm = torch.from_numpy(v).double() * m
+    conv = F.conv1d(F.pad(vm.transpose(1, 2), (5, 5)), torch.from_numpy(w).double().unsqueeze(1), groups=512).transpose(1, 2)
+    assert rel_err(got, conv + vm + torch.from_numpy(resid).double()) <= 2e-6
