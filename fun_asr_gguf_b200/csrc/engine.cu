@@ -30,6 +30,7 @@ void prof_before(const char* kernel, cudaStream_t st) {
     ProfRec r;
     r.name = kernel;
     if (!r.name.empty() && r.name[0] == '(') r.name.erase(0, 1);      // FA_LAUNCH((k<a, b>), ...) stringifies with its parentheses
+    if (!r.name.empty() && r.name.back() == ')') r.name.pop_back();
     const size_t lt = r.name.find('<');
     if (lt != std::string::npos && r.name.find("k_gemm_tc") == std::string::npos) r.name = r.name.substr(0, lt);
     r.flops = g_next_flops; r.bytes = g_next_bytes;

@@ -39,14 +39,16 @@ namespace {
 
 constexpr int BM = kTcBlockM, BN = kTcBlockN, BK = kTcBlockK;
 constexpr int kATileBytes = BM * BK * 2;         // 16 KB
-constexpr int kWTileBytes = BN * BK * 2;         // 32 KB
 constexpr int kThreads = 320;                   // TMA warp, MMA warp, 8 epilogue warps
 constexpr int kStagingBytes = 8 * 4096;         // one 4 KB transpose tile per epilogue warp
 constexpr uint32_t kTmemCols = 512;
 
-template <int NP> struct Cfg {
-    static constexpr int kStageBytes = NP * (kATileBytes + kWTileBytes);   // 96 KB (NP=2) / 48 KB (NP=1)
-    static constexpr int kStages = NP == 2 ? 2 : 4;
+// TN: columns of a tile of the single-CTA kernel.  256 is the throughput shape; 128 and 64 spread a small M (single-
+// segment calls: 8 row tiles) over more SMs and shorten the K loop, which is what the latency of such a call is made of.
+template <int NP, int TN = BN> struct Cfg {
+    static constexpr int kWBytes = TN * BK * 2;                              // 32 / 16 / 8 KB
+    static constexpr int kStageBytes = NP * (kATileBytes + kWBytes);        // TN = 256: 96 KB (NP=2) / 48 KB (NP=1)
+    static constexpr int kStages = 192 * 1024 / kStageBytes > 6 ? 6 : 192 * 1024 / kStageBytes;     // 2 / 4 at TN = 256
     static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -90,8 +92,7 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
            ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
-// cute::UMMA::InstrDescriptor: D=f32 (1<<4), A=B=bf16 (1<<7, 1<<10), K-major both, N>>3 @17, M>>4 @24.
-constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// cute::UMMA::InstrDescriptor: D=f32 (1<<4), A=B=bf16 (1<<7, 1<<10), K-major both, N>>3 @17, M>>4 @24 (built per kernel).
 
 __device__ __forceinline__ void tile_coords(int tile, int m_tiles, int n_tiles, int band, int& mt, int& nt) {
     // bands of `band` m-tiles; inside a band the n index is outermost so that the CTAs running together
@@ -290,12 +291,13 @@ __device__ __forceinline__ void epilogue_unit(const EpiParams& ep, const CUtenso
     }
 }
 
-template <int NP>
+template <int NP, int TN = BN>
 __global__ void __launch_bounds__(kThreads, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
           const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_pl, int m, int n, int k,
           int band, EpiParams ep) {
-    using C = Cfg<NP>;
+    using C = Cfg<NP, TN>;
+    constexpr uint32_t kIdescT = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t tiles_base = (raw + 1023u) & ~1023u;                      // SWIZZLE_128B wants 1024 B alignment
@@ -308,7 +310,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
 
     const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
-    const int m_tiles = (m + BM - 1) / BM, n_tiles = (n + BN - 1) / BN;
+    const int m_tiles = (m + BM - 1) / BM, n_tiles = (n + TN - 1) / TN;
     int num_tiles = m_tiles * n_tiles;
     const int k_blocks = (k + BK - 1) / BK;
 
@@ -354,7 +356,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 #pragma unroll
                     for (int p = 0; p < NP; ++p) {
                         tma_load_3d(sbase + p * kATileBytes, &map_a, full, kb * BK, mt * BM, p);
-                        tma_load_3d(sbase + NP * kATileBytes + p * kWTileBytes, &map_w, full, kb * BK, nt * BN, p);
+                        tma_load_3d(sbase + NP * kATileBytes + p * C::kWBytes, &map_w, full, kb * BK, nt * TN, p);
                     }
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }
@@ -378,22 +380,22 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                     tc_fence_after();
                     const uint32_t sbase = tiles_base + stage * C::kStageBytes;
                     const uint32_t a_hi = sbase, a_lo = sbase + kATileBytes;
-                    const uint32_t w_hi = sbase + NP * kATileBytes, w_lo = w_hi + kWTileBytes;
+                    const uint32_t w_hi = sbase + NP * kATileBytes, w_lo = w_hi + C::kWBytes;
                     uint32_t accum = kb > 0 ? 1u : 0u;
                     if constexpr (NP == 2) {
                         // small cross terms first, the dominant hi*hi term last
 #pragma unroll
                         for (int ks = 0; ks < BK / 16; ++ks) {
-                            tc_mma(tmem_d, umma_desc_sw128(a_lo + ks * 32), umma_desc_sw128(w_hi + ks * 32), kIdesc, accum);
+                            tc_mma(tmem_d, umma_desc_sw128(a_lo + ks * 32), umma_desc_sw128(w_hi + ks * 32), kIdescT, accum);
                             accum = 1u;
                         }
 #pragma unroll
                         for (int ks = 0; ks < BK / 16; ++ks)
-                            tc_mma(tmem_d, umma_desc_sw128(a_hi + ks * 32), umma_desc_sw128(w_lo + ks * 32), kIdesc, 1u);
+                            tc_mma(tmem_d, umma_desc_sw128(a_hi + ks * 32), umma_desc_sw128(w_lo + ks * 32), kIdescT, 1u);
                     }
 #pragma unroll
                     for (int ks = 0; ks < BK / 16; ++ks) {
-                        tc_mma(tmem_d, umma_desc_sw128(a_hi + ks * 32), umma_desc_sw128(w_hi + ks * 32), kIdesc, accum);
+                        tc_mma(tmem_d, umma_desc_sw128(a_hi + ks * 32), umma_desc_sw128(w_hi + ks * 32), kIdescT, accum);
                         accum = 1u;
                     }
                     tc_commit(bar_empty + 8 * stage);                 // smem stage free once these MMAs retire
@@ -414,7 +416,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             tile_coords(tile, m_tiles, n_tiles, band, mt, nt);
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            epilogue_unit(ep, &map_out, &map_pl, stg, store_pending, e, lane, m, n, mt * BM, nt * BN, BN, tmem_base + acc * BN,
+            epilogue_unit(ep, &map_out, &map_pl, stg, store_pending, e, lane, m, n, mt * BM, nt * TN, TN, tmem_base + acc * BN,
                           bar_tfull + 8 * acc, acc_phase);
             tc_fence_before();
             __syncwarp();
@@ -911,6 +913,8 @@ void tc_init_device() {
     });
     FA_CUDA(cudaFuncSetAttribute(k_gemm_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::kSmemBytes));
     FA_CUDA(cudaFuncSetAttribute(k_gemm_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::kSmemBytes));
+    FA_CUDA(cudaFuncSetAttribute((k_gemm_tc<2, 128>), cudaFuncAttributeMaxDynamicSharedMemorySize, (Cfg<2, 128>::kSmemBytes)));
+    FA_CUDA(cudaFuncSetAttribute((k_gemm_tc<2, 64>), cudaFuncAttributeMaxDynamicSharedMemorySize, (Cfg<2, 64>::kSmemBytes)));
     FA_CUDA(cudaFuncSetAttribute(k_gemm_tc2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<1>::kSmemBytes));
     FA_CUDA(cudaFuncSetAttribute(k_gemm_tc2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<2>::kSmemBytes));
     FA_CUDA(cudaFuncSetAttribute(k_gemm_tc2_ar, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgAR::kSmemBytes));
@@ -968,6 +972,7 @@ CUtensorMap make_store_map(CUtensorMapDataType dt, int elem_bytes, void* base, i
 TcOperand tc_make_weight(const __nv_bfloat16* base, int rows, int k, int64_t plane_stride_elems, int planes) {
     TcOperand op = tc_make_operand(base, rows, k, k, plane_stride_elems, planes, BN);
     op.map64 = tc_make_operand(base, rows, k, k, plane_stride_elems, planes, 64).map;
+    op.map128 = tc_make_operand(base, rows, k, k, plane_stride_elems, planes, 128).map;
     op.has64 = true;
     return op;
 }
@@ -1066,9 +1071,35 @@ void launch_gemm_tc(const TcOperand& a, const TcOperand& w, int m, int n, int k,
         }
         return;
     }
+    const int band = 16;
+    // Small M (calls of one to four segments): the latency of the call is the sum of ~310 dependent projections, each
+    // one round of tiles, so pick the tile width that makes that round shortest: K blocks x 12 instructions at 48 / 64 /
+    // 128 cycles (N = 64 / 128 / 256, tools/umma_bench) plus an epilogue of ~60 cycles per column, times the rounds the
+    // tiles need on the SMs there are.  FUNASR_B200_GEMM_TN=256 keeps the wide tiles (comparison aid).
+    if (n_planes == 2 && w.has64 && !ep.amax_val && !ep.cand_list) {
+        const char* tn_env = getenv("FUNASR_B200_GEMM_TN");
+        int best_tn = BN;
+        double best_cost = 0.0;
+        const int tns[3] = {256, 128, 64}, cyc[3] = {128, 64, 48};
+        for (int i = 0; i < 3; ++i) {
+            const int t = cdiv(m, BM) * cdiv(n, tns[i]);
+            const double cost = (double)cdiv(t, g_num_sms) * (cdiv(k, BK) * 12.0 * cyc[i] + 60.0 * tns[i]);
+            if (i == 0 || cost < best_cost) { best_cost = cost; best_tn = tns[i]; }
+        }
+        if (tn_env) best_tn = atoi(tn_env);
+        if (best_tn == 128 || best_tn == 64) {
+            const int t = cdiv(m, BM) * cdiv(n, best_tn);
+            const int g = t < g_num_sms ? t : g_num_sms;
+            if (best_tn == 128) {
+                FA_LAUNCH((k_gemm_tc<2, 128>), g, kThreads, (Cfg<2, 128>::kSmemBytes), st, a.map, w.map128, map_out, map_pl, m, n, k, band, ep);
+            } else {
+                FA_LAUNCH((k_gemm_tc<2, 64>), g, kThreads, (Cfg<2, 64>::kSmemBytes), st, a.map, w.map64, map_out, map_pl, m, n, k, band, ep);
+            }
+            return;
+        }
+    }
     const int tiles = cdiv(m, BM) * cdiv(n, BN);
     const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-    const int band = 16;
     if (n_planes == 2) {
         FA_LAUNCH(k_gemm_tc<2>, grid, kThreads, Cfg<2>::kSmemBytes, st, a.map, w.map, map_out, map_pl, m, n, k, band, ep);
     } else {

@@ -102,7 +102,8 @@ void launch_gemm_simt(const float* a, int lda, const float* w, int m, int n, int
 struct TcOperand {
     CUtensorMap map;        // 3D: {K, rows, planes}, box {64, box_rows, 1}, SWIZZLE_128B
     int rows = 0, k = 0, planes = 0;
-    CUtensorMap map64;      // weights only: the same tensor with 64-row boxes (CTA-pair kernel)
+    CUtensorMap map64;      // weights only: the same tensor with 64-row boxes (CTA-pair kernel, narrow tiles of the single-CTA kernel)
+    CUtensorMap map128;     // weights only: 128-row boxes (128-column tiles of the single-CTA kernel)
     bool has64 = false;
 };
 TcOperand tc_make_operand(const __nv_bfloat16* base, int rows, int k, int64_t row_stride_elems, int64_t plane_stride_elems,

@@ -459,6 +459,8 @@ k_ctc_collapse(const int32_t* __restrict__ ids, int frames, int blank, int32_t* 
 void launch_layernorm(const float* x, int rows, int d, const float* gamma, const float* beta, float eps,
                       const int* t_valid, int frames, float* y_f32, Planes y_pl, cudaStream_t st) {
     FA_REQUIRE(d % 4 == 0 && d <= 128 * kLnMaxVec, "layernorm width must be a multiple of 4 and <= 1024");
+    // algorithmic bytes: the row in, and whichever outputs are written (fp32 row, bf16 hi plane, bf16 lo plane)
+    prof_note_work(0.0, (double)rows * d * (4.0 + (y_f32 ? 4.0 : 0.0) + (y_pl.hi ? 2.0 : 0.0) + (y_pl.lo ? 2.0 : 0.0)));
     // d <= 512 (141 of the 155 launches of a step): one row per warp — 40 registers, 48 resident warps per SM; two rows
     // per warp (62 registers) measured 6 % slower on the same box, four rows 18 % slower
     if (d <= 512) {
@@ -477,6 +479,7 @@ void launch_fsmn(const float* v, int ldv, const float* w, const int* t_valid, in
                  const float* resid, float* out, cudaStream_t st) {
     FA_REQUIRE(ldv % 4 == 0, "fsmn input stride must be a multiple of 4");
     FA_REQUIRE(resid == nullptr || resid != v, "fsmn: the residual may alias the output, not the input");
+    prof_note_work(0.0, (double)batch * frames * kDenc * 4.0 * (resid ? 3.0 : 2.0));    // v in, residual in, x out
     const char* fe = getenv("FUNASR_B200_FSMN");                          // comparison aid, read at every launch
     const bool strips = !(fe && !strcmp(fe, "stream"));                     // the streaming kernel measured equal (4.07 vs 4.08 ms per step): strips stay the default
     static int sms = 0;

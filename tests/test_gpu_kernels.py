@@ -57,6 +57,27 @@ def test_linear_bias_relu_residual(raw, gemm_kernel, precision, m, n, k):
     assert np.abs(planes - got).max() <= 2.0 ** -15 * np.abs(got).max()
 
 
+@pytest.mark.parametrize("m,n,k", [(1001, 512, 512), (1001, 1536, 560), (1001, 512, 2048), (2002, 2048, 512), (300, 264, 128)])
+def test_linear_narrow_tiles_for_small_m_are_bit_identical_to_the_wide_tiles(raw, monkeypatch, m, n, k):
+    """Calls of one to four segments run the single-CTA kernel with 64- or 128-column tiles (more SMs, shorter K loop per
+    tile: the latency of such a call is the sum of ~310 dependent projections).  An output element sees the same
+    sequence of tensor-core products whatever the tile width, so the three widths must agree bit for bit."""
+    monkeypatch.setenv("FUNASR_B200_GEMM", "1cta")
+    a, w = _rand((m, k), 41), _rand((n, k), 42, k ** -0.5)
+    bias, resid = _rand((n,), 43), _rand((m, n), 44)
+    ref = torch.relu(torch.from_numpy(a).double() @ torch.from_numpy(w).double().t() + torch.from_numpy(bias).double())
+    ref = ref + torch.from_numpy(resid).double()
+    outs = {}
+    for tn in ("256", "128", "64"):
+        monkeypatch.setenv("FUNASR_B200_GEMM_TN", tn)
+        outs[tn] = raw.linear(a, w, bias, resid=resid, relu=True, precision="bf16x3", planes=True)
+    monkeypatch.delenv("FUNASR_B200_GEMM_TN")
+    outs["auto"] = raw.linear(a, w, bias, resid=resid, relu=True, precision="bf16x3", planes=True)
+    assert rel_err(outs["256"][0], ref) <= TOL["bf16x3"]
+    for tn in ("128", "64", "auto"):
+        assert np.array_equal(outs[tn][0], outs["256"][0]) and np.array_equal(outs[tn][1], outs["256"][1])
+
+
 @pytest.mark.parametrize("m,n,k", [(10240, 512, 512), (9999, 1536, 512), (20000, 512, 2048)])
 def test_linear_pair_kernel_full_waves_and_split_tail(raw, monkeypatch, m, n, k):
     """Sizes at which the library itself picks the CTA-pair kernel: several waves of 256 x 256 tiles and a
