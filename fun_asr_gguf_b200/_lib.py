@@ -36,6 +36,8 @@ SIGNATURES = {
     "fa_ctc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "fa_ctc_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "fa_front_half": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, c_i64_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fa_front_half_embd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, c_i64_p, C.c_void_p, C.POINTER(C.c_void_p), c_i64_p,
+                           C.c_void_p]),
     "fa_ctc_collapse_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fa_debug_enable_taps": (C.c_int, [C.c_void_p, C.c_int]),
     "fa_debug_read_tap": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, c_i64_p, c_i64_p]),

@@ -121,6 +121,14 @@ int fa_front_half(fa_ctx* ctx, const float* audio, int batch, int64_t samples, c
     });
 }
 
+int fa_front_half_embd(fa_ctx* ctx, const float* audio, int batch, int64_t samples, const int64_t* ilens, float* enc,
+                       float* const* embd_rows, int64_t* rows_out, int32_t* ids) {
+    return guarded([&] {
+        NEED(ctx); NEED(audio); NEED(ilens); NEED(embd_rows); NEED(ids);
+        ctx->impl.front_half_host(audio, batch, samples, ilens, enc, nullptr, ids, embd_rows, rows_out);
+    });
+}
+
 int fa_ctc_collapse_dev(fa_ctx* ctx, const int32_t* ids, int batch, int frames, int32_t* tokens, int32_t* starts,
                         int32_t* counts) {
     return guarded([&] {

@@ -771,10 +771,21 @@ void Context::ctc_host(const float* enc, int batch, int frames, int32_t* ids) {
 
 // ids == nullptr: encoder session only
 void Context::front_half_host(const float* audio, int batch, int64_t s_phys, const int64_t* ilens, float* enc,
-                              float* adaptor, int32_t* ids) {
+                              float* adaptor, int32_t* ids, float* const* embd_rows, int64_t* rows_out) {
     ensure_room(1, s_phys);
     set_device();
     const int frames = lfr_frames_of(s_phys);
+    if (embd_rows) adaptor = nullptr;
+    // embedding handoff: only the rows the LLM reads leave the device, straight to where the caller wants them
+    auto hand_off = [&](int b0, int nb, cudaStream_t st) {
+        for (int i = 0; embd_rows && i < nb; ++i) {
+            const int tl = target_len_of(ilens[b0 + i]);
+            if (rows_out) rows_out[b0 + i] = tl;
+            FA_REQUIRE(embd_rows[b0 + i] != nullptr, "embd_rows holds a null destination");
+            FA_CUDA(cudaMemcpyAsync(embd_rows[b0 + i], adaptor_out_.as<float>() + (size_t)i * frames * kDllm, (size_t)tl * kDllm * 4,
+                                    cudaMemcpyDefault, st));
+        }
+    };
     for (int b0 = 0; b0 < batch; b0 += max_batch_) {
         const int nb = std::min(max_batch_, batch - b0);
         stage_lengths(nb, s_phys, ilens + b0);
@@ -789,6 +800,7 @@ void Context::front_half_host(const float* audio, int batch, int64_t s_phys, con
             });
             if (enc) FA_CUDA(cudaMemcpyAsync(enc + (size_t)b0 * frames * kDenc, enc_.p, (size_t)nb * frames * kDenc * 4, cudaMemcpyDeviceToHost, stream_));
             if (adaptor) FA_CUDA(cudaMemcpyAsync(adaptor + (size_t)b0 * frames * kDllm, adaptor_out_.p, (size_t)nb * frames * kDllm * 4, cudaMemcpyDeviceToHost, stream_));
+            hand_off(b0, nb, stream_);
             if (ids) FA_CUDA(cudaMemcpyAsync(ids + (size_t)b0 * frames, ids_.p, (size_t)nb * frames * 4, cudaMemcpyDeviceToHost, stream_));
             FA_CUDA(cudaStreamSynchronize(stream_));
             continue;
@@ -797,6 +809,7 @@ void Context::front_half_host(const float* audio, int batch, int64_t s_phys, con
         encoder_graph(nb, s_phys, enc_.as<float>(), adaptor_out_.as<float>());
         if (enc) download_async(enc + (size_t)b0 * frames * kDenc, enc_.p, (size_t)nb * frames * kDenc * 4, ev_enc_);
         if (adaptor) download_async(adaptor + (size_t)b0 * frames * kDllm, adaptor_out_.p, (size_t)nb * frames * kDllm * 4, ev_ad_);
+        if (embd_rows) { FA_CUDA(cudaStreamWaitEvent(copy_stream_, ev_ad_, 0)); hand_off(b0, nb, copy_stream_); }
         if (ids) {
             ctc_dev(enc_.as<float>(), nb, frames, ids_.as<int32_t>());
             FA_CUDA(cudaMemcpyAsync(ids + (size_t)b0 * frames, ids_.p, (size_t)nb * frames * 4, cudaMemcpyDeviceToHost, stream_));

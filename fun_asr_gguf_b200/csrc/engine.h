@@ -77,8 +77,10 @@ public:
     // host-pointer executions (copies inside); synchronous
     void encode_host(const float* audio, int batch, int64_t s_phys, const int64_t* ilens, float* enc, float* adaptor);
     void ctc_host(const float* enc, int batch, int frames, int32_t* ids);
+    // embd_rows != nullptr: segment b's adaptor rows [0, target_len) go to embd_rows[b] (host or device memory) and
+    // rows_out[b] = target_len; `adaptor` is then ignored
     void front_half_host(const float* audio, int batch, int64_t s_phys, const int64_t* ilens, float* enc,
-                         float* adaptor, int32_t* ids);
+                         float* adaptor, int32_t* ids, float* const* embd_rows = nullptr, int64_t* rows_out = nullptr);
 
     void sync() { set_device(); FA_CUDA(cudaStreamSynchronize(stream_)); }
     void set_stream(cudaStream_t s);

@@ -108,6 +108,37 @@ class FrontHalf:
                                           _ptr(enc) if want_enc else None, _ptr(ad) if want_adaptor else None, _ptr(ids)))
         return enc, ad, ids
 
+    def front_half_into(self, audio: np.ndarray, ilens: Sequence[int], embd: np.ndarray, row_offset: int = 0,
+                        want_enc: bool = False):
+        """Embedding handoff.  Both graphs back to back; of each segment's adaptor_output only the rows
+        the LLM reads, [0, target_len), leave the device, written straight into ``embd`` — a C-contiguous float32
+        [rows][1024] array such as a numpy view of ``llama_batch.embd`` — one segment after another from ``row_offset``
+        (core/decoder.py:199 concatenates prefix, audio and suffix embeddings and llama.py:547 memmoves the result; here
+        the audio part lands in place).  Returns (rows per segment, ids [B][T], enc [B][T][512] or None)."""
+        audio = np.ascontiguousarray(audio, dtype=np.float32)
+        b, s = audio.shape
+        if not (isinstance(embd, np.ndarray) and embd.dtype == np.float32 and embd.ndim == 2 and embd.shape[1] == W.D_LLM
+                and embd.flags["C_CONTIGUOUS"] and embd.flags["WRITEABLE"]):
+            raise ValueError("embd must be a writable C-contiguous float32 array of shape [rows][1024]")
+        rows = [int(self.lib.fa_adaptor_rows_for_samples(int(n))) for n in ilens]
+        if len(rows) != b:
+            raise ValueError("ilens must have one entry per segment")
+        if row_offset < 0 or row_offset + sum(rows) > embd.shape[0]:
+            raise ValueError(f"embd has {embd.shape[0]} rows; {row_offset} + {sum(rows)} are needed")
+        t = self.frames(s)
+        enc = np.empty((b, t, W.D_ENC), np.float32) if want_enc else None
+        ids = np.empty((b, t), np.int32)
+        dst = (C.c_void_p * b)()
+        off = row_offset
+        for i, r in enumerate(rows):
+            dst[i] = embd.ctypes.data + off * W.D_LLM * 4
+            off += r
+        got = (C.c_int64 * b)()
+        _lib.check(self.lib.fa_front_half_embd(self._h, _ptr(audio), b, s, self._ilens(ilens, b),
+                                               _ptr(enc) if want_enc else None, dst, got, _ptr(ids)))
+        assert list(got) == rows
+        return rows, ids, enc
+
     # ------------------------------------------------------------------ device (torch.cuda) API
     def use_torch_stream(self):
         import torch

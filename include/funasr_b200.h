@@ -85,6 +85,15 @@ FA_API int fa_ctc_dev(fa_ctx* ctx, const float* enc_dev, int batch, int frames, 
 FA_API int fa_front_half(fa_ctx* ctx, const float* audio_host, int batch, int64_t samples, const int64_t* ilens,
                   float* enc_host, float* adaptor_host, int32_t* ids_host);
 
+/* ---- embedding handoff ----------------------------------------------------------------
+ * fa_front_half, except that of each segment's adaptor_output only the rows the LLM reads — [0, target_len), what
+ * nano_onnx.py:131-133 slices out — leave the device, written straight to embd_rows[b] (host or device memory,
+ * target_len x 1024 fp32, dense): e.g. into llama_batch.embd behind the prefix prompt's rows, instead of a
+ * [T][1024] array that the caller slices, concatenates with the prompt and memmoves (core/decoder.py:199,
+ * llama.py:536-547).  rows_out[b] = target_len (may be NULL); enc_host may be NULL. */
+FA_API int fa_front_half_embd(fa_ctx* ctx, const float* audio_host, int batch, int64_t samples, const int64_t* ilens,
+                       float* enc_host, float* const* embd_rows, int64_t* rows_out, int32_t* ids_host);
+
 /* ---- greedy collapse on device: the integer part of decode_ctc (nano_ctc.py:70-99) ----------------
  * ids [batch][frames] -> tokens/starts [batch][frames] (first counts[b] entries valid), blank = vocab-1 */
 FA_API int fa_ctc_collapse_dev(fa_ctx* ctx, const int32_t* ids_dev, int batch, int frames, int32_t* tokens_dev,

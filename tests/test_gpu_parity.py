@@ -222,6 +222,26 @@ def test_device_resident_api_matches_host_api(engine):
     assert np.array_equal(ids_d.cpu().numpy(), ids)
 
 
+def test_embedding_handoff_writes_only_the_rows_the_llm_reads(engine):
+    """fa_front_half_embd: the adaptor rows [0, target_len) of each segment land in a caller buffer at a
+    row offset — a stand-in for llama_batch.embd behind the prefix prompt — bit-identical to the slice the reference
+    takes from adaptor_output (nano_onnx.py:131-133); nothing else of the buffer is touched."""
+    a1, n1 = cases.build("padded5in8")
+    a2, n2 = cases.build("ragged")
+    s = max(a1.shape[0], a2.shape[0])
+    audio = np.stack([signals.padded(a1, s).numpy(), signals.padded(a2, s).numpy()])
+    enc, ad, ids = engine.front_half(audio, [n1, n2])
+    embd = np.full((400, Wm.D_LLM), 7.5, np.float32)
+    rows, ids2, enc2 = engine.front_half_into(audio, [n1, n2], embd, row_offset=11, want_enc=True)
+    assert rows == [Wm.adaptor_target_len(n1), Wm.adaptor_target_len(n2)]
+    assert np.array_equal(ids2, ids) and np.array_equal(enc2, enc)
+    assert np.array_equal(embd[11:11 + rows[0]], ad[0, :rows[0]])
+    assert np.array_equal(embd[11 + rows[0]:11 + rows[0] + rows[1]], ad[1, :rows[1]])
+    assert (embd[:11] == 7.5).all() and (embd[11 + sum(rows):] == 7.5).all()
+    with pytest.raises(ValueError):
+        engine.front_half_into(audio, [n1, n2], embd[:20], row_offset=11)
+
+
 def test_bad_arguments_raise(engine):
     audio = np.zeros((1, 2 * SR), np.float32)
     with pytest.raises(RuntimeError):
