@@ -117,12 +117,25 @@ def _find_checkpoint(model_path: str) -> Optional[str]:
     return None
 
 
+def precision_for(model_path: str) -> str:
+    """The reference ships three builds of each graph and picks one by file name (02-Quantize-ONNX.py:14,34;
+    04-Inference.py:42-43 defaults to ``.fp16.onnx``): ``.fp32.`` the traced FP32 graph, ``.fp16.`` everything but
+    LayerNorm in half precision, ``.int8.`` per-channel dynamic QUInt8 MatMuls.  Here: the fp32 and fp16
+    names run the bf16x3 mode — 16 mantissa bits per operand, i.e. at least the fp16 graph's accuracy and token-exact
+    against the FP32 one — and the int8 name, whose user has asked for speed at ~2^-8 per operand, runs the one-product
+    bf16 mode (same operand precision class, 1.3x the throughput).  ``$FUNASR_B200_PRECISION`` overrides."""
+    env = os.environ.get("FUNASR_B200_PRECISION")
+    if env:
+        return env
+    return "bf16" if ".int8." in os.path.basename(model_path).lower() else "bf16x3"
+
+
 def _engine_for(model_path: str, min_samples: int = 0):
     from .engine import FrontHalf
 
     ckpt = _find_checkpoint(model_path)
     device = int(os.environ.get("FUNASR_B200_DEVICE", "0"))
-    precision = os.environ.get("FUNASR_B200_PRECISION", "bf16x3")
+    precision = precision_for(model_path)
     max_batch = int(os.environ.get("FUNASR_B200_MAX_BATCH", "4"))
     key = (ckpt or "random:0", device, precision)
     with _lock:

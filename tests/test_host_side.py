@@ -120,6 +120,16 @@ def test_shim_surface(shim):
         ctc.run(["logits"], {"enc_output": e})
 
 
+def test_model_file_name_selects_the_precision_mode(monkeypatch):
+    """02-Quantize-ONNX.py:14,34 names the variants; 04-Inference.py:42-43 loads the fp16 ones by default."""
+    monkeypatch.delenv("FUNASR_B200_PRECISION", raising=False)
+    assert ort_shim.precision_for("m/Fun-ASR-Nano-Encoder-Adaptor.fp32.onnx") == "bf16x3"
+    assert ort_shim.precision_for("m/Fun-ASR-Nano-Encoder-Adaptor.fp16.onnx") == "bf16x3"
+    assert ort_shim.precision_for("m/Fun-ASR-Nano-CTC.int8.onnx") == "bf16"
+    monkeypatch.setenv("FUNASR_B200_PRECISION", "fp32")
+    assert ort_shim.precision_for("m/Fun-ASR-Nano-CTC.int8.onnx") == "fp32"
+
+
 @pytest.mark.skipif(not os.path.isdir(REF), reason="/root/reference not mounted")
 def test_unmodified_reference_call_sites_run_on_the_shim(shim, weights, consts):
     """load_onnx_models / encode_audio / decode_ctc of the reference, byte-for-byte, over our sessions."""
