@@ -112,14 +112,22 @@ class FrontHalf:
                         want_enc: bool = False):
         """Embedding handoff.  Both graphs back to back; of each segment's adaptor_output only the rows
         the LLM reads, [0, target_len), leave the device, written straight into ``embd`` — a C-contiguous float32
-        [rows][1024] array such as a numpy view of ``llama_batch.embd`` — one segment after another from ``row_offset``
+        [rows][1024] numpy array such as a view of ``llama_batch.embd``, or a torch tensor in host or device memory — one segment after another from ``row_offset``
         (core/decoder.py:199 concatenates prefix, audio and suffix embeddings and llama.py:547 memmoves the result; here
         the audio part lands in place).  Returns (rows per segment, ids [B][T], enc [B][T][512] or None)."""
         audio = np.ascontiguousarray(audio, dtype=np.float32)
         b, s = audio.shape
-        if not (isinstance(embd, np.ndarray) and embd.dtype == np.float32 and embd.ndim == 2 and embd.shape[1] == W.D_LLM
-                and embd.flags["C_CONTIGUOUS"] and embd.flags["WRITEABLE"]):
-            raise ValueError("embd must be a writable C-contiguous float32 array of shape [rows][1024]")
+        if isinstance(embd, np.ndarray):
+            ok = (embd.dtype == np.float32 and embd.ndim == 2 and embd.shape[1] == W.D_LLM and embd.flags["C_CONTIGUOUS"]
+                  and embd.flags["WRITEABLE"])
+            base = embd.ctypes.data if ok else 0
+        else:                                   # a torch tensor, host or CUDA (the copy is cudaMemcpyDefault)
+            import torch
+            ok = (isinstance(embd, torch.Tensor) and embd.dtype == torch.float32 and embd.dim() == 2
+                  and embd.shape[1] == W.D_LLM and embd.is_contiguous())
+            base = embd.data_ptr() if ok else 0
+        if not ok:
+            raise ValueError("embd must be a writable C-contiguous float32 array or tensor of shape [rows][1024]")
         rows = [int(self.lib.fa_adaptor_rows_for_samples(int(n))) for n in ilens]
         if len(rows) != b:
             raise ValueError("ilens must have one entry per segment")
@@ -131,7 +139,7 @@ class FrontHalf:
         dst = (C.c_void_p * b)()
         off = row_offset
         for i, r in enumerate(rows):
-            dst[i] = embd.ctypes.data + off * W.D_LLM * 4
+            dst[i] = base + off * W.D_LLM * 4
             off += r
         got = (C.c_int64 * b)()
         _lib.check(self.lib.fa_front_half_embd(self._h, _ptr(audio), b, s, self._ilens(ilens, b),

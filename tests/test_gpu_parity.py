@@ -240,6 +240,11 @@ def test_embedding_handoff_writes_only_the_rows_the_llm_reads(engine):
     assert (embd[:11] == 7.5).all() and (embd[11 + sum(rows):] == 7.5).all()
     with pytest.raises(ValueError):
         engine.front_half_into(audio, [n1, n2], embd[:20], row_offset=11)
+    # the same into device memory (what a CUDA build of llama.cpp would hand over)
+    dev = torch.full((400, Wm.D_LLM), 7.5, dtype=torch.float32, device="cuda:0")
+    rows_d, ids_d, _ = engine.front_half_into(audio, [n1, n2], dev, row_offset=11)
+    torch.cuda.synchronize()
+    assert rows_d == rows and np.array_equal(ids_d, ids) and np.array_equal(dev.cpu().numpy(), embd)
 
 
 def test_bad_arguments_raise(engine):
