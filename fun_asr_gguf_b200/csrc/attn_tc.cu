@@ -37,11 +37,13 @@
 //                S = Q K^T (M128 x N128) into two score tiles, O += P V (M128 x N d_k, V from smem MN-major:
 //                no transpose).  The tensor pipe executes in issue order, which is what lets S(j+2) reuse
 //                the tile P(j) lives in without a barrier: it is issued after P(j) V(j).
-//   warps 2..17  softmax: 4 groups of 4 warps.  Group g works on key tiles j with (j & 1) == (g >> 1), score
-//                tile g >> 1, keys 64 (g & 1) .. +63 of the tile (a warp can only touch its own quarter of the
-//                TMEM lanes, so the split is by columns): thread = query row = TMEM lane; tcgen05.ld 32 scores,
-//                exp2 / sum, split p into hi/lo planes, tcgen05.st over the same 32 columns.  The groups
-//                exchange row maxima after pass 1 and their row sums are added by the epilogue.
+//   warps 2..17  softmax: 4 groups of 4 warps.  Every key tile is shared by all sixteen warps: group g owns keys
+//                32 g .. 32 g + 31 of each tile (a warp can only touch its own quarter of the TMEM lanes, so the split
+//                is by columns): thread = query row = TMEM lane; tcgen05.ld 32 scores, exp2 / sum, split p into hi/lo
+//                planes, tcgen05.st over the same 32 columns.  (Two groups per tile, 64 keys per thread on alternate
+//                tiles, has fewer hand-offs but twice the latency from "scores complete" to "weights written", which is
+//                exposed at the head and the tail of every item: 188 -> 182 us per encoder launch.)  The groups exchange
+//                row maxima once per item and their row sums are added by the epilogue.
 //   warps 18..21 query loader (global -> registers -> TMEM, next item's Q while the current item finishes
 //                its PV products) and output epilogue (O / l -> bf16 planes or fp32)
 // TMEM columns: score/weight tile 0 at 0, tile 1 at 128, O at 256, Q at 384 (hi d_k/2 | lo d_k/2).
@@ -126,8 +128,8 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
     if (threadIdx.x == 0) {
         for (int s = 0; s < kSlots; ++s) { mbar_init(bar_kvfull + 8 * s, 1); mbar_init(bar_kvempty + 8 * s, 1); }
         for (int s = 0; s < 2; ++s) {
-            mbar_init(bar_sfull + 8 * s, 1); mbar_init(bar_sempty + 8 * s, 8);
-            mbar_init(bar_pfull + 8 * s, 8);
+            mbar_init(bar_sfull + 8 * s, 1); mbar_init(bar_sempty + 8 * s, 16);
+            mbar_init(bar_pfull + 8 * s, 16);
             mbar_init(bar_lfull + 8 * s, 16);
         }
         mbar_init(bar_qfull, 4); mbar_init(bar_qlofull, 4); mbar_init(bar_qempty, 1);
@@ -384,35 +386,32 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
         }
     } else if (warp < 18) {
         // ================================================================== softmax (4 groups of 4 warps)
+        // Every key tile is shared by all sixteen warps: group g4 owns keys 32*g4 .. +31 of each tile, so the latency from
+        // "scores complete" to "weights written" is that of 32 columns per thread on four warps per SM sub-partition.
         const int g4 = (warp - 2) >> 2;                             // group 0..3
-        const int grp = g4 >> 1, half = g4 & 1;                     // key tiles j with (j & 1) == grp; keys 64*half.. of the tile
         const int quarter = warp & 3;
         const int r = quarter * 32 + lane;                          // query row in the tile == TMEM lane
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-        const uint32_t tmem_s = tmem_base + lane_addr + C::kSCol + grp * KT + half * 64;
-        const uint32_t sfull = bar_sfull + 8 * grp, sempty = bar_sempty + 8 * grp, pfull = bar_pfull + 8 * grp;
-        uint32_t item_it = 0, su = 0;
-        // row maximum of this thread's 64 keys of the score tile at tmem_s (keys kbase .. kbase+63, those < klen)
-        auto tile_max = [&](int kbase, int klen, float mx) {
+        const uint32_t tmem_s = tmem_base + lane_addr + C::kSCol + g4 * 32;     // + (j & 1) * KT for key tile j
+        uint32_t item_it = 0, su0 = 0, su1 = 0;                      // waits so far on "scores ready" of score tile 0 / 1
+        // row maximum of this thread's 32 keys of the score tile at `ts` (keys kbase .. kbase+31, those < klen)
+        auto tile_max = [&](uint32_t ts, int kbase, int klen, float mx) {
+            uint32_t s[32];
+            tc_ld32(ts, s);
+            tc_wait_ld();
+            if (kbase + 32 <= klen) {
+                float m4[4] = {mx, -INFINITY, -INFINITY, -INFINITY};      // four short chains instead of one of 16
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint32_t s[32];
-                tc_ld32(tmem_s + c * 32, s);
-                tc_wait_ld();
-                if (kbase + c * 32 + 32 <= klen) {
-                    float m4[4] = {mx, -INFINITY, -INFINITY, -INFINITY};      // four short chains instead of one of 16
+                for (int i = 0; i < 32; i += 8) {
 #pragma unroll
-                    for (int i = 0; i < 32; i += 8) {
-#pragma unroll
-                        for (int a = 0; a < 4; ++a)
-                            m4[a] = fmaxf(m4[a], fmaxf(__uint_as_float(s[i + 2 * a]), __uint_as_float(s[i + 2 * a + 1])));
-                    }
-                    mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (kbase + c * 32 + i < klen) mx = fmaxf(mx, __uint_as_float(s[i]));
+                    for (int a = 0; a < 4; ++a)
+                        m4[a] = fmaxf(m4[a], fmaxf(__uint_as_float(s[i + 2 * a]), __uint_as_float(s[i + 2 * a + 1])));
                 }
+                mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (kbase + i < klen) mx = fmaxf(mx, __uint_as_float(s[i]));
             }
             return mx;
         };
@@ -423,29 +422,28 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
             float* mxb = mx_smem + (item_it & 1) * 4 * QT;           // buffers alternate by item parity
             if (warp == 2) trace(item_it, 16);
             if (!exact) {
-                // ---- fast mode: the shift is the row maximum over key tile 0 (the two groups that own it), taken from
-                // the exact scores pass 2 is about to turn into weights
-                if (grp == 0) {
-                    mbar_wait(sfull, su & 1);                        // S(0); the pass-2 loop waits on it again (at once)
-                    if (warp == 2) trace(item_it, 17);
-                    tc_fence_after();
-                    mx = tile_max(half * 64, klen, mx);
-                    if (warp == 2) trace(item_it, 18);
-                }
+                // ---- fast mode: the shift is the row maximum over key tile 0, taken from the exact scores pass 2 is
+                // about to turn into weights
+                mbar_wait(bar_sfull, su0 & 1);                       // S(0); the pass-2 loop waits on it again (at once)
+                if (warp == 2) trace(item_it, 17);
+                tc_fence_after();
+                mx = tile_max(tmem_s, g4 * 32, klen, mx);
+                if (warp == 2) trace(item_it, 18);
                 mxb[g4 * QT + r] = mx;
                 asm volatile("bar.sync 1, 512;" ::: "memory");
-                mx = fmaxf(mxb[r], mxb[QT + r]);
+                mx = fmaxf(fmaxf(mxb[r], mxb[QT + r]), fmaxf(mxb[2 * QT + r], mxb[3 * QT + r]));
                 if (warp == 2) trace(item_it, 19);
             }
-            // ---- pass 1 (sharing every tile among all sixteen warps, 32 keys each, was measured and is slower: the
-            // fixed cost of a hand-off per tile per warp outweighs the shorter read)
-            for (int j = grp; exact && j < n; j += 2, ++su) {
-                mbar_wait(sfull, su & 1);
+            // ---- pass 1 (exact mode)
+            for (int j = 0; exact && j < n; ++j) {
+                uint32_t& su = (j & 1) ? su1 : su0;
+                mbar_wait(bar_sfull + 8 * (j & 1), su & 1);
+                ++su;
                 tc_fence_after();
-                mx = tile_max(j * KT + half * 64, klen, mx);
+                mx = tile_max(tmem_s + (j & 1) * KT, j * KT + g4 * 32, klen, mx);
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(sempty);                 // these scores may be overwritten
+                if (lane == 0) mbar_arrive(bar_sempty + 8 * (j & 1));    // these scores may be overwritten
             }
             if (exact) {
                 // the four groups saw disjoint keys: exchange the row maxima
@@ -453,37 +451,39 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
                 asm volatile("bar.sync 1, 512;" ::: "memory");
                 mx = fmaxf(fmaxf(mxb[r], mxb[QT + r]), fmaxf(mxb[2 * QT + r], mxb[3 * QT + r]));
             }
-            // ---- pass 2: scores -> weights in place, 32 keys at a time
+            // ---- pass 2: scores -> weights in place
             float lsum = 0.f;
-            for (int j = grp; j < n; j += 2, ++su) {
-                mbar_wait(sfull, su & 1);
+            for (int j = 0; j < n; ++j) {
+                uint32_t& su = (j & 1) ? su1 : su0;
+                mbar_wait(bar_sfull + 8 * (j & 1), su & 1);
+                ++su;
                 tc_fence_after();
-                const int kbase = j * KT + half * 64;
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
+                const int kbase = j * KT + g4 * 32;
+                const uint32_t ts = tmem_s + (j & 1) * KT;
+                {
                     uint32_t s[32];
-                    tc_ld32(tmem_s + c * 32, s);
+                    tc_ld32(ts, s);
                     tc_wait_ld();
-                    const bool full_chunk = kbase + c * 32 + 32 <= klen;
+                    const bool full_chunk = kbase + 32 <= klen;
                     uint32_t hi[16], lo[16];                         // 32 keys x bf16, packed in pairs (even key in the low half)
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         float p0 = fast_exp2(__uint_as_float(s[2 * i]) - mx);
                         float p1 = fast_exp2(__uint_as_float(s[2 * i + 1]) - mx);
                         if (!full_chunk) {
-                            if (kbase + c * 32 + 2 * i >= klen) p0 = 0.f;
-                            if (kbase + c * 32 + 2 * i + 1 >= klen) p1 = 0.f;
+                            if (kbase + 2 * i >= klen) p0 = 0.f;
+                            if (kbase + 2 * i + 1 >= klen) p1 = 0.f;
                         }
                         lsum += p0 + p1;
                         split_bf16x2(p0, p1, hi[i], lo[i]);
                     }
-                    tc_st16(tmem_s + c * 32, hi);
-                    tc_st16(tmem_s + c * 32 + 16, lo);
+                    tc_st16(ts, hi);
+                    tc_st16(ts + 16, lo);
                 }
                 tc_wait_st();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(pfull);
+                if (lane == 0) mbar_arrive(bar_pfull + 8 * (j & 1));
                 if (warp == 2 && j < 2) trace(item_it, 20);
             }
             // ---- hand this group's row sums to the epilogue warps
