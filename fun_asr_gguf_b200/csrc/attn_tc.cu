@@ -31,7 +31,7 @@
 // tile is 128 keys, so every instruction is N = 128.
 //
 // One CTA per SM, persistent over (segment, head, 128-query tile) items:
-//   warp 0       TMA: one plane of a 128-key K or V tile per ring slot (6 slots), in the order the MMA warp
+//   warp 0       TMA: one plane of a 128-key K or V tile per ring slot (128 KB of slots), in the order the MMA warp
 //                consumes them; pass 1 loads the hi plane of K only
 //   warp 1       TMEM allocator + MMA issuer (all lanes walk the loop, one elected lane issues):
 //                S = Q K^T (M128 x N128) into two score tiles, O += P V (M128 x N d_k, V from smem MN-major:
@@ -45,7 +45,9 @@
 //                exposed at the head and the tail of every item: 188 -> 182 us per encoder launch.)  The groups exchange
 //                row maxima once per item and their row sums are added by the epilogue.
 //   warps 18..21 query loader (global -> registers -> TMEM, next item's Q while the current item finishes
-//                its PV products) and output epilogue (O / l -> bf16 planes or fp32)
+//                its PV products) and output epilogue: O / l -> bf16 hi/lo planes, staged in shared memory as the
+//                source tiles of bulk tensor stores, so that O is handed back after four TMEM loads and no warp
+//                waits for global stores (fp32 rows, the kernel tests' other output form, go straight from registers)
 // TMEM columns: score/weight tile 0 at 0, tile 1 at 128, O at 256, Q at 384 (hi d_k/2 | lo d_k/2).
 // Inside a score tile, keys 32c .. 32c+31 become: hi pairs in columns 32c .. +15, lo pairs in 32c+16 .. +31.
 #include "kernels.h"
@@ -53,6 +55,8 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <string>
 #include <vector>
 
 namespace fa {
@@ -62,15 +66,19 @@ namespace {
 constexpr int QT = 128;          // queries per item (UMMA M)
 constexpr int KT = 128;          // keys per tile (UMMA N for S, K extent for PV)
 constexpr int kAttThreads = 704;
-constexpr int kSlots = 6;
+// K/V ring: 128 KB of one-plane tiles (4 slots at d_k = 128, 8 at d_k = 64).  At d_k = 128 a ring of 4, 5 or 6 slots
+// measured the same; the other 64 KB stage the output.  At d_k = 64 a key tile is half the tensor time, so the same ring
+// in BYTES is what keeps the loads as far ahead in time (4 slots there: 236 -> 249 us).
 constexpr int kRedoWords = 64;       // one bit per item of a CTA's sequence (2048 items per CTA)
-constexpr bool kAttnTiming = false;
-constexpr bool kAttnTrace = false;    // tuning aid: clock64 stamps of CTA 0's roles per item (set true, rebuild, FUNASR_B200_ATTN_TIMING=1)   // tuning aid: set true, rebuild, run with FUNASR_B200_ATTN_TIMING=1 (per-cause wait cycles of the MMA warp)
+constexpr bool kAttnTiming = false;   // tuning aid: set true, rebuild, run with FUNASR_B200_ATTN_TIMING=1 (per-cause wait cycles of the MMA warp)
+constexpr bool kAttnTrace = false;    // tuning aid: clock64 stamps of CTA 0's roles per item (set true, rebuild, FUNASR_B200_ATTN_TIMING=1)
 
 template <int DK> struct ACfg {
     static constexpr int kChunks = DK / 64;                  // 128-byte column chunks per head row
     static constexpr int kSlotBytes = kChunks * KT * 128;    // one plane of a 128-key tile of K (or V)
-    static constexpr int kSmemBytes = kSlots * kSlotBytes + 16 * QT * 4 /*row sums and maxima*/ + kRedoWords * 4 + 1024 + 256;
+    static constexpr int kSlots = 4 * 32768 / kSlotBytes;
+    static constexpr int kStageBytes = 4 * 16384;           // per loader warp: its 32 rows of O as bf16 hi/lo planes, 64-column boxes
+    static constexpr int kSmemBytes = kSlots * kSlotBytes + 16 * QT * 4 /*row sums and maxima*/ + kStageBytes + kRedoWords * 4 + 1024 + 256;
     static constexpr uint32_t kTmemCols = 512;
     static constexpr uint32_t kSCol = 0, kOCol = 256, kQCol = 384;
     static constexpr uint32_t kQPlaneCols = DK / 2;          // packed bf16 pairs
@@ -83,6 +91,12 @@ __device__ __forceinline__ float fast_exp2(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 struct AttnParams {
     int batch, frames, heads, d_model, ld;     // ld = row stride (elements) of the qkv planes
@@ -99,16 +113,17 @@ struct AttnParams {
 
 template <int DK>
 __global__ void __launch_bounds__(kAttThreads, 1)
-k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
+k_attention_tc(const __grid_constant__ CUtensorMap map_kv, const __grid_constant__ CUtensorMap map_out, AttnParams p) {
     using C = ACfg<DK>;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t kv_base = (raw + 1023u) & ~1023u;
-    const uint32_t l_base = kv_base + kSlots * C::kSlotBytes;              // float[2 item parities][4 groups][128]: row sums, then row maxima
-    const uint32_t redo_base = l_base + 16 * QT * 4;                       // uint32[kRedoWords]: items to repeat with the exact shift
+    const uint32_t l_base = kv_base + C::kSlots * C::kSlotBytes;              // float[2 item parities][4 groups][128]: row sums, then row maxima
+    const uint32_t stage_base = l_base + 16 * QT * 4;                      // 1024-aligned: tensor-store source tiles (SWIZZLE_128B)
+    const uint32_t redo_base = stage_base + C::kStageBytes;                      // uint32[kRedoWords]: items to repeat with the exact shift
     const uint32_t bars = redo_base + kRedoWords * 4;
-    const uint32_t bar_kvfull = bars, bar_kvempty = bars + 8 * kSlots;   // [kSlots] each
-    const uint32_t bar_sfull = bars + 16 * kSlots, bar_sempty = bar_sfull + 16;   // [2] each
+    const uint32_t bar_kvfull = bars, bar_kvempty = bars + 8 * C::kSlots;   // [C::kSlots] each
+    const uint32_t bar_sfull = bars + 16 * C::kSlots, bar_sempty = bar_sfull + 16;   // [2] each
     const uint32_t bar_pfull = bar_sempty + 16;                          // [2]
     const uint32_t bar_qfull = bar_pfull + 16, bar_qempty = bar_qfull + 8;   // hi plane of Q in TMEM (all pass 1 needs)
     const uint32_t bar_ofull = bar_qempty + 8, bar_oempty = bar_ofull + 8;
@@ -126,7 +141,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
 
     if (threadIdx.x < kRedoWords) redo_bits[threadIdx.x] = 0u;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kSlots; ++s) { mbar_init(bar_kvfull + 8 * s, 1); mbar_init(bar_kvempty + 8 * s, 1); }
+        for (int s = 0; s < C::kSlots; ++s) { mbar_init(bar_kvfull + 8 * s, 1); mbar_init(bar_kvempty + 8 * s, 1); }
         for (int s = 0; s < 2; ++s) {
             mbar_init(bar_sfull + 8 * s, 1); mbar_init(bar_sempty + 8 * s, 16);
             mbar_init(bar_pfull + 8 * s, 16);
@@ -137,6 +152,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_async_smem();
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_kv) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_out) : "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, C::kTmemCols);
     tc_fence_before();
@@ -185,7 +201,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
         uint32_t cnt = 0;                             // slots produced so far: slot = cnt % kSlots
         // plane `pl` of the 128-key tile of K (which = 1) or V (which = 2) starting at `row`, into the next ring slot
         auto load_plane = [&](int which, int pl, int h, int row) {
-            const uint32_t slot = cnt % kSlots, ph = (cnt / kSlots) & 1;
+            const uint32_t slot = cnt % C::kSlots, ph = (cnt / C::kSlots) & 1;
             mbar_wait(bar_kvempty + 8 * slot, ph ^ 1);
             const uint32_t full = bar_kvfull + 8 * slot, sb = kv_base + slot * C::kSlotBytes;
             if (elect_one()) {
@@ -242,7 +258,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
         const long long dbg_t0 = kAttnTiming ? clock64() : 0;
         auto take = [&](uint32_t& s_out, uint32_t& ph_out) {
             s_out = slot; ph_out = slot_ph;
-            if (++slot == kSlots) { slot = 0; slot_ph ^= 1; }
+            if (++slot == C::kSlots) { slot = 0; slot_ph ^= 1; }
         };
         // one product Q(plane) K(plane)^T into the score tile: DK/16 instructions
         auto s_term = [&](uint32_t tile, uint32_t qcol, uint32_t kpl, uint32_t first_accum) {
@@ -534,7 +550,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
         uint32_t qw[kQW];
         // this role looks one item ahead, so it walks the two phases of the sequence (see FA_ATT_SEQUENCE_BEGIN) by hand
         for (int second = 0; second < 2; ++second) {
-            if (second) asm volatile("bar.sync 2, %0;" ::"n"(kAttThreads) : "memory");
+            if (second) { bulk_wait_all0(); asm volatile("bar.sync 2, %0;" ::"n"(kAttThreads) : "memory"); }   // a repeated item rewrites its rows
             const bool exact = second || p.force_exact != 0;
             auto in_phase = [&](int kk) { return !second || (((redo_bits[kk >> 5] >> (kk & 31)) & 1u) != 0u); };
             auto advance = [&](int& it, int& kk) { do { it += gridDim.x; ++kk; } while (it < items && !in_phase(kk)); };
@@ -602,6 +618,52 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
                     }
                 }
             };
+            if (p.ctx_hi && !p.ctx) {
+                // The engine's form of the output: bf16 hi/lo planes.  The warp turns its 32 rows of O into planes 32
+                // columns at a time and parks them in shared memory, laid out as the source tiles of bulk tensor stores
+                // (64-column boxes, 128-byte rows, SWIZZLE_128B); O goes back to the MMA warp as soon as the last columns
+                // are in registers, and no warp ever waits for a global store — the stores of all CTAs arrive at the
+                // memory system in the same microsecond (the items of a launch run in lockstep) and used to hold the
+                // hand-back for ~6 k cycles of every item.
+                unsigned char* stg = smem_raw + (stage_base - raw) + (warp - 18) * 16384;
+                const uint32_t stg_u32 = stage_base + (warp - 18) * 16384;
+                if (lane == 0) bulk_wait_read0();                    // the previous item's stores have read the tiles (an item ago)
+                __syncwarp();
+#pragma unroll 1
+                for (int c = 0; c < DK / 32; ++c) {
+                    uint32_t o[32];
+                    tc_ld32(tmem_base + lane_addr + C::kOCol + c * 32, o);
+                    tc_wait_ld();
+                    if (c + 1 == DK / 32) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_oempty);
+                        if (warp == 18) trace(item_it, 13);
+                    }
+                    uint32_t hw[16], lw[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        split_bf16x2(__uint_as_float(o[2 * i]) * inv, __uint_as_float(o[2 * i + 1]) * inv, hw[i], lw[i]);
+                    unsigned char* box = stg + (c >> 1) * 8192;          // hi tile, then lo tile, of this 64-column box
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int off = lane * 128 + (((4 * (c & 1) + i) ^ (lane & 7)) << 4);
+                        *reinterpret_cast<uint4*>(box + off) = make_uint4(hw[4 * i], hw[4 * i + 1], hw[4 * i + 2], hw[4 * i + 3]);
+                        *reinterpret_cast<uint4*>(box + 4096 + off) = make_uint4(lw[4 * i], lw[4 * i + 1], lw[4 * i + 2], lw[4 * i + 3]);
+                    }
+                }
+                fence_async_smem();
+                __syncwarp();
+                const int row0 = qt * QT + quarter * 32;
+                if (lane == 0 && row0 < p.frames) {                  // rows past the segment's end are clipped by the map
+#pragma unroll
+                    for (int bx = 0; bx < DK / 64; ++bx) {
+                        tma_store_4d(&map_out, stg_u32 + bx * 8192, h * DK + bx * 64, row0, b, 0);
+                        if (p.ctx_lo) tma_store_4d(&map_out, stg_u32 + bx * 8192 + 4096, h * DK + bx * 64, row0, b, 1);
+                    }
+                    bulk_commit();
+                }
+            } else {
 #pragma unroll 1
             for (int c = 0; c < DK / 32; c += 2) {
                 uint32_t o0[32], o1[32];
@@ -617,12 +679,14 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
                 emit(o0, c);
                 emit(o1, c + 1);
             }
+            }
             if (warp == 18) trace(item_it, 14);
             ++item_it;
             item = next;
             k = next_k;
             }
         }
+        bulk_wait_all0();                                           // this thread's bulk stores have been written
     }
 
     tc_fence_before();
@@ -638,9 +702,40 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, AttnParams p) {
 
 int g_att_sms = 0;
 
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_att_encode = nullptr;
+std::once_flag g_att_once;
+
+// Store map of the output planes: {model column, frame of the segment, segment, plane}, boxes of 64 columns x 32 rows.
+// Frames past the end of a segment are clipped by the map.
+CUtensorMap att_out_map(Planes out, int ldo, int d_model, int frames, int batch) {
+    FA_REQUIRE(g_att_encode != nullptr, "attention_tc_init_device() has not run");
+    FA_REQUIRE((reinterpret_cast<uintptr_t>(out.hi) & 15) == 0, "TMA base must be 16-byte aligned");
+    const int64_t plane_stride = out.lo ? (out.lo - out.hi) : (int64_t)batch * frames * ldo;
+    FA_REQUIRE(plane_stride > 0 && plane_stride % 8 == 0, "attention output planes: lo must follow hi at a multiple of 8 elements");
+    const cuuint64_t dims[4] = {(cuuint64_t)d_model, (cuuint64_t)frames, (cuuint64_t)batch, (cuuint64_t)(out.lo ? 2 : 1)};
+    const cuuint64_t strides[3] = {(cuuint64_t)ldo * 2, (cuuint64_t)frames * ldo * 2, (cuuint64_t)plane_stride * 2};
+    const cuuint32_t box[4] = {64, 32, 1, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUtensorMap m;
+    const CUresult r = g_att_encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out.hi, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw Error("cuTensorMapEncodeTiled (attention output) failed with code " + std::to_string((int)r));
+    return m;
+}
+
 }  // namespace
 
 void attention_tc_init_device() {
+    std::call_once(g_att_once, [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        FA_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        FA_REQUIRE(fn != nullptr && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available in this driver");
+        g_att_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    });
     FA_CUDA(cudaFuncSetAttribute(k_attention_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, ACfg<128>::kSmemBytes));
     FA_CUDA(cudaFuncSetAttribute(k_attention_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ACfg<64>::kSmemBytes));
     int dev = 0;
@@ -664,6 +759,9 @@ void launch_attention_tc(Planes qkv, int64_t plane_stride, int ld, int d_model, 
         const char* sh = getenv("FUNASR_B200_ATTENTION_SHIFT");      // comparison aid, read at every launch
         p.force_exact = (sh && !strcmp(sh, "exact")) ? 1 : 0;
     }
+    CUtensorMap map_out;
+    memset(&map_out, 0, sizeof(map_out));
+    if (ctx_pl.hi && !ctx_f32) map_out = att_out_map(ctx_pl, ldo, d_model, frames, batch);
     const int items = batch * heads * cdiv(frames, QT);
     int grid = items < g_att_sms ? items : g_att_sms;
     if (const char* e = getenv("FUNASR_B200_ATT_SMS")) { const int v = atoi(e); if (v > 0 && v < grid) grid = v; }   // tuning aid: fewer CTAs
@@ -676,9 +774,9 @@ void launch_attention_tc(Planes qkv, int64_t plane_stride, int ld, int d_model, 
     }
     prof_note_work(4.0 * batch * heads * (double)frames * frames * dk, 0.0);
     if (dk == 128) {
-        FA_LAUNCH(k_attention_tc<128>, grid, kAttThreads, ACfg<128>::kSmemBytes, st, mkv.map, p);
+        FA_LAUNCH(k_attention_tc<128>, grid, kAttThreads, ACfg<128>::kSmemBytes, st, mkv.map, map_out, p);
     } else {
-        FA_LAUNCH(k_attention_tc<64>, grid, kAttThreads, ACfg<64>::kSmemBytes, st, mkv.map, p);
+        FA_LAUNCH(k_attention_tc<64>, grid, kAttThreads, ACfg<64>::kSmemBytes, st, mkv.map, map_out, p);
     }
     if (timing) {       // tuning aid only: synchronises
         std::vector<long long> h((size_t)grid * 16);
