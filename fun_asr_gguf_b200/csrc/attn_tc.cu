@@ -765,6 +765,8 @@ void launch_attention_tc(Planes qkv, int64_t plane_stride, int ld, int d_model, 
     const int items = batch * heads * cdiv(frames, QT);
     int grid = items < g_att_sms ? items : g_att_sms;
     if (const char* e = getenv("FUNASR_B200_ATT_SMS")) { const int v = atoi(e); if (v > 0 && v < grid) grid = v; }   // tuning aid: fewer CTAs
+    // the repeat bitmap holds one bit per item of a CTA's sequence; more would spill into the barriers behind it
+    FA_REQUIRE(cdiv(items, grid) <= 32 * kRedoWords, "attention: too many items per CTA for the repeat bitmap");
     static const bool timing = (kAttnTiming || kAttnTrace) && getenv("FUNASR_B200_ATTN_TIMING") != nullptr;
     long long* dbg = nullptr;
     if (timing) {
@@ -773,6 +775,7 @@ void launch_attention_tc(Planes qkv, int64_t plane_stride, int ld, int d_model, 
         p.dbg = dbg;
     }
     prof_note_work(4.0 * batch * heads * (double)frames * frames * dk, 0.0);
+    if (g_prof_on) prof_note_tag(dk == 128 ? "dk128" : "dk64");
     if (dk == 128) {
         FA_LAUNCH(k_attention_tc<128>, grid, kAttThreads, ACfg<128>::kSmemBytes, st, mkv.map, map_out, p);
     } else {

@@ -43,6 +43,7 @@ extern thread_local bool g_prof_on;
 void prof_before(const char* kernel, cudaStream_t st);
 void prof_after(cudaStream_t st);
 void prof_note_work(double flops, double bytes);   // algorithmic work of the next launch
+void prof_note_tag(const char* tag);               // shape class of the next launch (profile key suffix)
 // Every launch carries the programmatic-stream-serialization attribute: the next kernel's CTAs may be placed
 // and run their prologue (barrier init, TMEM allocation, descriptor prefetch) while the previous kernel drains;
 // each kernel calls grid_dependency_wait() before it touches global memory.  FUNASR_B200_PDL=0 turns it off.

@@ -22,9 +22,13 @@ namespace {
 struct ProfRec { std::string name; cudaEvent_t a, b; double flops, bytes; };
 thread_local std::vector<ProfRec> g_prof;
 thread_local double g_next_flops = 0.0, g_next_bytes = 0.0;
+thread_local std::string g_next_tag;
 }  // namespace
 
 void prof_note_work(double flops, double bytes) { g_next_flops = flops; g_next_bytes = bytes; }
+// Shape class of the next launch ("n1536_k512", "gated", ...): appended to the kernel's name in the profile so that
+// bench.py can report each class of one kernel against its own roofline.
+void prof_note_tag(const char* tag) { if (g_prof_on) g_next_tag = tag; }
 
 void prof_before(const char* kernel, cudaStream_t st) {
     ProfRec r;
@@ -33,6 +37,7 @@ void prof_before(const char* kernel, cudaStream_t st) {
     if (!r.name.empty() && r.name.back() == ')') r.name.pop_back();
     const size_t lt = r.name.find('<');
     if (lt != std::string::npos && r.name.find("k_gemm_tc") == std::string::npos) r.name = r.name.substr(0, lt);
+    if (!g_next_tag.empty()) { r.name += "/" + g_next_tag; g_next_tag.clear(); }
     r.flops = g_next_flops; r.bytes = g_next_bytes;
     g_next_flops = g_next_bytes = 0.0;
     FA_CUDA(cudaEventCreate(&r.a));
@@ -75,13 +80,6 @@ std::string prof_end() {
 }
 
 namespace {
-constexpr int kLenSlots = 4;
-struct LenRing {
-    cudaEvent_t ev[kLenSlots];
-    int next = 0;
-};
-std::map<const Context*, LenRing> g_rings;
-
 int lfr_frames_of(int64_t samples) { return (int)((samples / kHop + 1 + kLfrN - 1) / kLfrN); }
 int target_len_of(int64_t n_valid) {
     const int t = lfr_frames_of(n_valid);
@@ -124,18 +122,13 @@ Context::Context(int device, int max_batch, int64_t max_samples, int precision)
     t_mel_max_ = (int)(max_samples / kHop + 1);
     t_max_ = lfr_frames_of(max_samples);
     m_max_ = (int64_t)max_batch * t_max_;
-    LenRing& r = g_rings[this];
-    for (auto& e : r.ev) FA_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : len_ev_) FA_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 }
 
 Context::~Context() {
     cudaSetDevice(device_);
     cudaDeviceSynchronize();
-    auto it = g_rings.find(this);
-    if (it != g_rings.end()) {
-        for (auto& e : it->second.ev) cudaEventDestroy(e);
-        g_rings.erase(it);
-    }
+    for (auto& e : len_ev_) if (e) cudaEventDestroy(e);
     for (auto& kv : graphs_) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     if (h_lens_) cudaFreeHost(h_lens_);
     for (auto& ev : ev_up_) if (ev) cudaEventDestroy(ev);
@@ -548,10 +541,9 @@ void Context::projector(const Projector& P, const Act& in, int batch, int frames
 // ------------------------------------------------------------------------------------ graphs
 
 void Context::stage_lengths(int batch, int64_t s_phys, const int64_t* h_ilens) {
-    LenRing& ring = g_rings[this];
-    const int slot = ring.next;
-    ring.next = (ring.next + 1) % kLenSlots;
-    FA_CUDA(cudaEventSynchronize(ring.ev[slot]));
+    const int slot = len_next_;
+    len_next_ = (len_next_ + 1) % kLenSlots;
+    FA_CUDA(cudaEventSynchronize(len_ev_[slot]));
     int* hl = h_lens_ + (size_t)slot * 3 * max_batch_;
     for (int b = 0; b < batch; ++b) {
         const int64_t nv = h_ilens[b];
@@ -561,7 +553,7 @@ void Context::stage_lengths(int batch, int64_t s_phys, const int64_t* h_ilens) {
         hl[2 * max_batch_ + b] = target_len_of(nv);
     }
     FA_CUDA(cudaMemcpyAsync(lens_.p, hl, (size_t)3 * max_batch_ * sizeof(int), cudaMemcpyHostToDevice, stream_));
-    FA_CUDA(cudaEventRecord(ring.ev[slot], stream_));
+    FA_CUDA(cudaEventRecord(len_ev_[slot], stream_));
 }
 
 // a1-a2 for segments b0 .. b0+nb-1 of the batch (segments are independent): waveform -> log-mel
@@ -708,6 +700,9 @@ void Context::vocab_argmax(const float* x, Planes x_pl, const Linear& lo, float 
     // a short batch would spread every row over many concurrent pairs, each starting its running maximum from
     // nothing: long lists for flat logits and no time to win back, so it keeps the three-product projection
     const bool use_cand = cand.list && 2 * cdiv(m, 2 * kTcBlockM) >= tc_num_pairs();
+    // either way the decision is the fp32 argmax over rescored columns (kernels.h), so a segment's ids do not depend
+    // on how many segments share the call; the one-product speed mode keeps the plain combine
+    const bool rescore_slots = cand.list != nullptr;
     if (use_cand) {
         launch_vocab_prepare(x, m, lo.k, w_norm_max, x_pl, cand, stream_);
         e.cand = cand;
@@ -716,13 +711,17 @@ void Context::vocab_argmax(const float* x, Planes x_pl, const Linear& lo, float 
         Epilogue e2;
         e2.bias = lo.b; e2.amax_val = amax_val; e2.amax_idx = amax_idx; e2.gate = cand.overflowed;
         launch_gemm_tc(opa, lo.op, m, lo.n, lo.k, 2, e2, stream_);
-        launch_argmax_combine(amax_val, amax_idx, m, tc_argmax_tiles(lo.n), d_ids, stream_, cand.count, cand.cap);
+        launch_vocab_rescore_slots(x, lo.w, lo.b, m, lo.k, lo.n, w_norm_max, amax_val, tc_argmax_tiles(lo.n), d_ids, stream_,
+                                   cand.count, cand.cap);
         return;
     }
     launch_split_planes(x, (int64_t)m * lo.k, x_pl, stream_);
     e.amax_val = amax_val; e.amax_idx = amax_idx;
     launch_gemm_tc(opa, lo.op, m, lo.n, lo.k, prec_ == kBf16x3 ? 2 : 1, e, stream_);
-    launch_argmax_combine(amax_val, amax_idx, m, tc_argmax_tiles(lo.n), d_ids, stream_);
+    if (rescore_slots && prec_ == kBf16x3)
+        launch_vocab_rescore_slots(x, lo.w, lo.b, m, lo.k, lo.n, w_norm_max, amax_val, tc_argmax_tiles(lo.n), d_ids, stream_);
+    else
+        launch_argmax_combine(amax_val, amax_idx, m, tc_argmax_tiles(lo.n), d_ids, stream_);
 }
 
 void Context::collapse_dev(const int32_t* d_ids, int batch, int frames, int32_t* d_tokens, int32_t* d_starts,
@@ -758,6 +757,9 @@ void Context::encode_host(const float* audio, int batch, int64_t s_phys, const i
 }
 
 void Context::ctc_host(const float* enc, int batch, int frames, int32_t* ids) {
+    // checked before the first copy: an oversized `frames` must not write past the workspace
+    FA_REQUIRE(finalized_, "context not finalized");
+    FA_REQUIRE(batch >= 1 && frames >= 1 && frames <= t_max_, "CTC input exceeds the context's capacity");
     set_device();
     for (int b0 = 0; b0 < batch; b0 += max_batch_) {
         const int nb = std::min(max_batch_, batch - b0);

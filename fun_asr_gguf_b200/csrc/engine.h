@@ -165,6 +165,9 @@ private:
     int* d_tvalid_ = nullptr;
     int* d_tlen_ = nullptr;
     int* h_lens_ = nullptr;      // pinned staging for the three length vectors
+    static constexpr int kLenSlots = 4;       // ring of staging slots: a slot is reused once its upload has completed
+    cudaEvent_t len_ev_[kLenSlots] = {};
+    int len_next_ = 0;
     int logits_rows_ = 0;
     struct GraphEntry { cudaGraphExec_t exec = nullptr; int64_t launches = 0; };
     std::map<std::tuple<int, int, int64_t>, GraphEntry> graphs_;

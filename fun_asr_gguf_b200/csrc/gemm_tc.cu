@@ -1031,7 +1031,16 @@ void launch_gemm_tc(const TcOperand& a, const TcOperand& w, int m, int n, int k,
         const cuuint64_t strides[2] = {(cuuint64_t)e.ldp * 2, (cuuint64_t)plane_stride * 2};
         map_pl = make_store_map(CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ep.out_hi, 3, dims, strides, CU_TENSOR_MAP_SWIZZLE_64B);
     }
-    prof_note_work(2.0 * m * (double)n * k, 0.0);
+    // A gated launch whose gate is closed executes nothing: it is booked at 0 FLOP under its own key (the gate is
+    // only known on the device; the second-chance vocabulary pass is the one gated launch and its gate is closed
+    // unless a candidate list overflowed).
+    prof_note_work(e.gate ? 0.0 : 2.0 * m * (double)n * k, 0.0);
+    if (g_prof_on) {
+        char tag[64];
+        if (e.gate) snprintf(tag, sizeof tag, "gated");
+        else snprintf(tag, sizeof tag, "n%d_k%d", n, k);
+        prof_note_tag(tag);
+    }
     // CTA pairs (256 x 256 tiles) once there is at least a full wave of them; below that the 128-row
     // tiles of the single-CTA kernel spread a small M over twice as many SMs.
     const int pair_tiles = cdiv(m, 2 * BM) * cdiv(n, BN);

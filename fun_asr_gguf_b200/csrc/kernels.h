@@ -128,6 +128,11 @@ int tc_num_pairs();      // CTA pairs of the tcgen05 GEMM that run at once (74 o
 void launch_vocab_prepare(const float* x, int rows, int d, float w_norm_max, Planes x_pl, VocabCand c, cudaStream_t st);
 void launch_vocab_rescore(const float* x, const float* w, const float* bias, int rows, int d, int n, VocabCand c, int32_t* ids,
                           cudaStream_t st);
+// the three-product projection's partial maxima (one slot per 128 columns) decided by the same fp32 rescoring: every
+// column of the slots within the three-product error bound of the row's best is rescored, first maximal index wins
+void launch_vocab_rescore_slots(const float* x, const float* w, const float* bias, int rows, int d, int n, float w_norm_max,
+                                const float* pmax, int slots, int32_t* ids, cudaStream_t st,
+                                const int32_t* only_if_over = nullptr, int over = 0);
 // max over rows of |w_row|_2, left in *out (device)
 void launch_row_norm_max(const float* w, int rows, int d, float* out, cudaStream_t st);
 

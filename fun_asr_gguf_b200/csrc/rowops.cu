@@ -363,6 +363,20 @@ k_vocab_prepare(const float* __restrict__ x, int rows, int d, float w_norm_max, 
     }
 }
 
+// fp32 logit of one column, by one warp: fixed lane / shuffle order, so every path that rescores a column gets the same bits
+__device__ __forceinline__ float vocab_score(const float* __restrict__ xr, const float* __restrict__ w,
+                                             const float* __restrict__ bias, int col, int d, int lane) {
+    const float* wr = w + (int64_t)col * d;
+    float s = 0.f;
+    for (int i = lane * 4; i < d; i += 128) {
+        const float4 a = *reinterpret_cast<const float4*>(xr + i);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(wr + i));
+        s = fmaf(a.x, b.x, s); s = fmaf(a.y, b.y, s); s = fmaf(a.z, b.z, s); s = fmaf(a.w, b.w, s);
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    return __fadd_rn(s, bias[col]);
+}
+
 // One warp per row.  The list holds every column that was within bound2 of the running maximum when its tile was
 // finished; only those within bound2 of the FINAL approximate maximum can hold the true maximum, and only they are
 // rescored: an fp32 dot product in a fixed lane / shuffle order, so the result does not depend on the
@@ -384,18 +398,6 @@ k_vocab_rescore(const float* __restrict__ x, const float* __restrict__ w, const 
     const float thr = ord2f(run_max[row]) - bound2[row];
     float bv = -INFINITY;
     int bi = 0x7fffffff;
-    auto score = [&](int col) {
-        const float* wr = w + (int64_t)col * d;
-        float s = 0.f;
-        for (int i = lane * 4; i < d; i += 128) {
-            const float4 a = *reinterpret_cast<const float4*>(xr + i);
-            const float4 b = __ldg(reinterpret_cast<const float4*>(wr + i));
-            s = fmaf(a.x, b.x, s); s = fmaf(a.y, b.y, s); s = fmaf(a.z, b.z, s); s = fmaf(a.w, b.w, s);
-        }
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        s = __fadd_rn(s, bias[col]);
-        amax_merge(bv, bi, s, col);
-    };
     for (int c0 = 0; c0 < cnt; c0 += 32) {
         int2 e = make_int2(0, 0);
         bool keep = false;
@@ -407,7 +409,49 @@ k_vocab_rescore(const float* __restrict__ x, const float* __restrict__ w, const 
         while (live) {
             const int src = __ffs(live) - 1;
             live &= live - 1;
-            score(__shfl_sync(0xffffffffu, e.x, src));
+            const int col = __shfl_sync(0xffffffffu, e.x, src);
+            amax_merge(bv, bi, vocab_score(xr, w, bias, col, d, lane), col);
+        }
+    }
+    if (lane == 0) ids[row] = bi;
+}
+
+// The three-product projection's per-128-column partial maxima (small batches, and the second-chance pass of the
+// candidate path) decided the same way: every 128-column slot whose partial maximum is within the three-product
+// error bound of the row's best may hold the true fp32 maximum, so ALL columns of those slots (one or two, as a rule)
+// are rescored with vocab_score and the first maximal index wins.  Both vocabulary paths therefore return the argmax
+// of the same fp32 scores: the ids of a segment do not depend on how many segments share the call.
+// |L - L3| <= 3 * 2^-17 (1 + eps) sum |x_i||w_i| + accumulation rounding  <=  2^-15 |x| |w|; the test uses twice that.
+__global__ void __launch_bounds__(256)
+k_vocab_rescore_slots(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, int rows, int d,
+                      int n, float w_norm_max, const float* __restrict__ pmax, int slots, int32_t* __restrict__ ids,
+                      const int32_t* __restrict__ only_if_over, int over) {
+    grid_dependency_wait();
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    if (only_if_over && only_if_over[row] <= over) return;
+    const float* xr = x + (int64_t)row * d;
+    float s2 = 0.f, mx = -INFINITY;
+    for (int i = lane * 4; i < d; i += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(xr + i);
+        s2 = fmaf(v.x, v.x, s2); s2 = fmaf(v.y, v.y, s2); s2 = fmaf(v.z, v.z, s2); s2 = fmaf(v.w, v.w, s2);
+    }
+    for (int t = lane; t < slots; t += 32) mx = fmaxf(mx, pmax[(int64_t)row * slots + t]);
+    for (int o = 16; o > 0; o >>= 1) {
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    const float thr = mx - 2.0f * 0x1p-15f * sqrtf(s2) * w_norm_max;
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int t0 = 0; t0 < slots; t0 += 32) {
+        const int t = t0 + lane;
+        unsigned live = __ballot_sync(0xffffffffu, t < slots && pmax[(int64_t)row * slots + t] >= thr);
+        while (live) {
+            const int slot = t0 + __ffs(live) - 1;
+            live &= live - 1;
+            const int c1 = min(n, (slot + 1) * 128);
+            for (int col = slot * 128; col < c1; ++col) amax_merge(bv, bi, vocab_score(xr, w, bias, col, d, lane), col);
         }
     }
     if (lane == 0) ids[row] = bi;
@@ -533,6 +577,14 @@ void launch_vocab_rescore(const float* x, const float* w, const float* bias, int
     FA_REQUIRE(d % 4 == 0, "vocab_rescore needs a width that is a multiple of 4");
     FA_LAUNCH(k_vocab_rescore, cdiv(rows, 8), 256, 0, st, x, w, bias, rows, d, n, c.run_max, c.count, c.bound2, c.list, c.cap, ids,
               c.overflowed);
+}
+
+void launch_vocab_rescore_slots(const float* x, const float* w, const float* bias, int rows, int d, int n, float w_norm_max,
+                                const float* pmax, int slots, int32_t* ids, cudaStream_t st, const int32_t* only_if_over,
+                                int over) {
+    FA_REQUIRE(d % 4 == 0, "vocab_rescore_slots needs a width that is a multiple of 4");
+    FA_LAUNCH(k_vocab_rescore_slots, cdiv(rows, 8), 256, 0, st, x, w, bias, rows, d, n, w_norm_max, pmax, slots, ids, only_if_over,
+              over);
 }
 
 void launch_ctc_collapse(const int32_t* ids, int batch, int frames, int blank, int32_t* tokens, int32_t* starts,

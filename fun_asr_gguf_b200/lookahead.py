@@ -73,6 +73,8 @@ class FrontCache:
             self._by_enc.pop(id(old.enc_output), None)
 
     def encoder_lookup(self, audio_phys: np.ndarray, n_valid: int) -> Optional[SegmentFront]:
+        if not self._by_audio:               # nothing was prefetched: do not hash 3.8 MB per call for a certain miss
+            return None
         seg = self._by_audio.get(_key(audio_phys, n_valid))
         if seg is not None and seg.n_phys == audio_phys.shape[0]:
             self.hits += 1
@@ -81,7 +83,7 @@ class FrontCache:
 
     def ctc_lookup(self, enc: np.ndarray) -> Optional[SegmentFront]:
         """The CTC session is fed the very array the encoder session returned (core/decoder.py:27)."""
-        seg = self._by_enc.get(id(enc))
+        seg = self._by_enc.get(id(enc)) if self._by_enc else None
         if seg is not None and seg.enc_output is enc:
             self.hits += 1
             return seg

@@ -130,7 +130,21 @@ def precision_for(model_path: str) -> str:
     return "bf16" if ".int8." in os.path.basename(model_path).lower() else "bf16x3"
 
 
+_tensors: Dict[tuple, "object"] = {}      # checkpoint tensors by key: growing an engine does not re-read the file
+
+
+def samples_for_frames(frames: int) -> int:
+    """Fewest samples whose segment has `frames` LFR frames: ceil((s//160 + 1) / 6) >= T  <=>  s >= (6T - 6) * 160."""
+    return max(1, (W.LFR_N * frames - W.LFR_N) * W.HOP)
+
+
 def _engine_for(model_path: str, min_samples: int = 0):
+    """The engine the sessions of `model_path` share, with room for segments of `min_samples`.
+
+    Sessions call this on EVERY run and never keep the result: when a longer segment than planned for arrives the
+    engine is replaced (the new one is built first, then the old one is closed), and a session holding on to the old
+    one would be left with a closed context.  Capacity is rounded up to whole seconds, so the CTC session's request
+    for the frames the encoder session just produced never forces a second rebuild."""
     from .engine import FrontHalf
 
     ckpt = _find_checkpoint(model_path)
@@ -141,18 +155,24 @@ def _engine_for(model_path: str, min_samples: int = 0):
     with _lock:
         eng = _engines.get(key)
         want = max(min_samples, int(os.environ.get("FUNASR_B200_MAX_SECONDS", "62")) * W.SAMPLE_RATE)
-        if eng is not None and eng.max_samples < want:
-            eng.close()          # a longer segment than planned for: rebuild with more room
-            eng = None
-        if eng is None:
+        want = -(-want // W.SAMPLE_RATE) * W.SAMPLE_RATE
+        if eng is not None and eng.max_samples >= want:
+            return eng
+        tensors = _tensors.get(key)
+        if tensors is None:
             if ckpt is None:
                 log.warning("no FunASR checkpoint near %s: using seeded random-init weights of the architecture", model_path)
                 tensors = W.random_weights(0)
             else:
                 tensors = W.load_checkpoint(ckpt)
-            eng = FrontHalf(tensors, device=device, max_batch=max_batch, max_samples=want, precision=precision)
-            _engines[key] = eng
-        return eng
+            _tensors[key] = tensors
+        if eng is not None:
+            log.info("segment of %d samples exceeds the engine's %d: rebuilding with more room", min_samples, eng.max_samples)
+        new = FrontHalf(tensors, device=device, max_batch=max_batch, max_samples=want, precision=precision)
+        _engines[key] = new
+        if eng is not None:
+            eng.close()
+        return new
 
 
 def shutdown() -> None:
@@ -160,6 +180,7 @@ def shutdown() -> None:
         for e in _engines.values():
             e.close()
         _engines.clear()
+        _tensors.clear()
 
 
 # --------------------------------------------------------------------------------------- sessions
@@ -175,7 +196,7 @@ class InferenceSession:
         self._options = sess_options or SessionOptions()
         self._requested = list(providers or [])
         self._role = "ctc" if "ctc" in os.path.basename(self._path).lower() else "encoder"
-        self._engine = _engine_for(self._path)
+        _engine_for(self._path)                  # builds (or finds) the shared context now, like ORT loads the model now
         if self._role == "encoder":
             self._inputs = [NodeArg("audio", "tensor(float)", [1, 1, "samples"]),
                             NodeArg("ilens", "tensor(int64)", ["batch"])]
@@ -219,9 +240,7 @@ class InferenceSession:
                 hit = lookahead.cache().encoder_lookup(audio.reshape(s), int(ilens[0]))
                 if hit is not None:
                     return {"enc_output": hit.enc_output, "adaptor_output": hit.adaptor_output}
-            if s > self._engine.max_samples:
-                self._engine = _engine_for(self._path, min_samples=s)
-            enc, ad = self._engine.encode(audio.reshape(b, s).astype(np.float32, copy=False), ilens.tolist())
+            enc, ad = _engine_for(self._path, min_samples=s).encode(audio.reshape(b, s).astype(np.float32, copy=False), ilens.tolist())
             return {"enc_output": enc, "adaptor_output": ad}
         if "enc_output" not in feed:
             raise ValueError("Required input 'enc_output' is missing")
@@ -233,9 +252,8 @@ class InferenceSession:
                 return {"indices": hit.ids}
         if enc.ndim != 3 or enc.shape[2] != W.D_ENC:
             raise ValueError(f"enc_output must be (batch, frames, {W.D_ENC}); got {enc.shape}")
-        if enc.shape[1] > self._engine.frames(self._engine.max_samples):
-            self._engine = _engine_for(self._path, min_samples=enc.shape[1] * W.LFR_N * W.HOP)
-        return {"indices": self._engine.ctc(enc.astype(np.float32, copy=False))}
+        eng = _engine_for(self._path, min_samples=samples_for_frames(enc.shape[1]))
+        return {"indices": eng.ctc(enc.astype(np.float32, copy=False))}
 
     def run(self, output_names, input_feed: Dict[str, np.ndarray], run_options=None):
         return self._select(output_names, self._run(dict(input_feed)))

@@ -1,6 +1,7 @@
 """Generate tests/golden/*.npz by running the REFERENCE's own modules (build container only).
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py            # the parity cases (reference_outputs.*)
+    python tests/golden/make_golden.py --bench32  # the 32 x 60 s batch bench.py measures on (bench32_outputs.*)
 
 Needs /root/reference (read-only mount).  The reference's model_definition.py is executed in
 PyTorch eager FP32 with the seeded weights of fun_asr_gguf_b200.weights.random_weights(0)
@@ -85,5 +86,46 @@ def main():
         json.dump(meta, f, indent=1, sort_keys=True)
 
 
+def bench32():
+    """The batch bench.py's default workload times (BASELINE configs[1]): 32 x 60 s of white noise, seeds 1234 + i.
+    Pins per row: ids (random-init and planted CTC projection), the top-2 margins, and every 200th enc row."""
+    torch.set_num_threads(os.cpu_count())
+    from fun_asr_gguf_b200 import synth
+    w = Wm.random_weights(0)
+    consts = Wm.front_end_constants(1100)
+    wp = planted.plant(w, consts)
+    # the structured-audio plant leaves white noise on one id; a plant calibrated on white noise makes the ids of the
+    # benchmark's own signals change almost every frame
+    wpw = planted.plant(w, consts, cal=synth.white(6 * cases.SR, 9999))
+    ref, ref_p, ref_pw = ref_harness.Reference(w), ref_harness.Reference(wp), ref_harness.Reference(wpw)
+    n = 60 * cases.SR
+    blobs = {k: [] for k in ("ids", "ids_planted", "ids_planted_white", "margin", "margin_planted", "margin_planted_white",
+                             "enc_rows", "adaptor_rows")}
+    for i in range(32):
+        audio = synth.white(n, i)
+        enc, ad = ref.encode(audio, n)
+        lg, lgp, lgw = ref.ctc_logits(enc), ref_p.ctc_logits(enc), ref_pw.ctc_logits(enc)
+        t2, t2p, t2w = lg.topk(2, -1).values, lgp.topk(2, -1).values, lgw.topk(2, -1).values
+        blobs["ids_planted_white"].append(lgw.argmax(-1).to(torch.int32).numpy())
+        blobs["margin_planted_white"].append((t2w[:, 0] - t2w[:, 1]).numpy())
+        blobs["ids"].append(lg.argmax(-1).to(torch.int32).numpy())
+        blobs["ids_planted"].append(lgp.argmax(-1).to(torch.int32).numpy())
+        blobs["margin"].append((t2[:, 0] - t2[:, 1]).numpy())
+        blobs["margin_planted"].append((t2p[:, 0] - t2p[:, 1]).numpy())
+        blobs["enc_rows"].append(enc[::200].numpy())
+        blobs["adaptor_rows"].append(ad[:126:25].numpy())
+        assert np.array_equal(blobs["ids"][-1], ref.ctc_ids(enc).numpy())
+        print(i, len(np.unique(blobs["ids"][-1])), len(np.unique(blobs["ids_planted"][-1])), len(np.unique(blobs["ids_planted_white"][-1])),
+              float(blobs["margin_planted_white"][-1].min()), flush=True)
+    np.savez_compressed(os.path.join(OUT, "bench32_outputs.npz"), **{k: np.stack(v) for k, v in blobs.items()})
+    with open(os.path.join(OUT, "bench32_outputs.json"), "w") as f:
+        json.dump({"oracle": "reference model_definition.py, PyTorch eager FP32, CPU (not ONNX Runtime)", "torch": torch.__version__,
+                   "signal": "fun_asr_gguf_b200.synth.white(960000, i), i = 0..31 (bench.py rank 0, first input set)",
+                   "enc_row_stride": 200, "adaptor_row_stride": 25, "weights_seed": 0}, f, indent=1, sort_keys=True)
+
+
 if __name__ == "__main__":
-    main()
+    if "--bench32" in sys.argv:
+        bench32()
+    else:
+        main()

@@ -4,10 +4,9 @@ reference pins, on a B200.
 Tolerances (stated here as the north star requires):
   enc_output / adaptor_output : max |cuda - oracle| <= ACT_TOL[precision] (absolute; activations are O(1..5))
       fp32   2e-4   — same arithmetic as the oracle up to summation order, through 72 layers
-      bf16x3 1e-3   — 2^-16-per-product operand rounding through 72 layers
-  CTC ids : identical to the oracle on every frame whose oracle top-2 logit margin exceeds
-      MARGIN_TOL (near-ties are inherent to any re-execution, SURVEY §7 hard part 1); the strict
-      mismatch count is always printed, and must be <= 1 % of frames.
+      bf16x3 3e-4   — 2^-16-per-product operand rounding through 72 layers (observed maxima are printed; ~1.2e-4)
+  CTC ids : IDENTICAL to the oracle / the reference pins on every frame of every committed case (strict == 0).  The
+      smallest oracle top-2 margin of each case is printed as a diagnostic of how close a case comes to a tie.
 """
 import numpy as np
 import pytest
@@ -20,9 +19,14 @@ from tests import cases, signals
 
 pytestmark = pytest.mark.gpu
 
-ACT_TOL = {"fp32": 2e-4, "bf16x3": 1e-3}
-MARGIN_TOL = {"fp32": 2e-4, "bf16x3": 1e-3}
+ACT_TOL = {"fp32": 2e-4, "bf16x3": 3e-4}
 SR = 16000
+
+
+def _act_close(got, ref, precision, what):
+    err = float(np.abs(got - ref).max())
+    print(f"[{what}/{precision}] max |cuda - reference| = {err:.3e} (tolerance {ACT_TOL[precision]:.0e})")
+    assert err <= ACT_TOL[precision], what
 
 
 @pytest.fixture(scope="module", params=["fp32", "bf16x3"])
@@ -37,10 +41,8 @@ def _check_ids(ids, logits, precision, what):
     top2 = logits.topk(2, -1).values
     margin = (top2[:, 0] - top2[:, 1]).numpy()
     strict = int((ids != ref).sum())
-    clear = margin > MARGIN_TOL[precision]
     print(f"[{what}/{precision}] strict id mismatches {strict}/{len(ref)}; min margin {margin.min():.2e}")
-    assert np.array_equal(ids[clear], ref[clear])
-    assert strict <= max(1, len(ref) // 100)
+    assert strict == 0, what
 
 
 @pytest.mark.parametrize("name", list(cases.CASES))
@@ -51,12 +53,13 @@ def test_case_matches_oracle_and_reference_pins(name, engine, golden, weights, c
     enc, ad, ids = engine.front_half(audio.numpy()[None], [n_valid])
     enc_o, ad_o = O.encode_one(audio, n_valid, weights, consts)
     # against the oracle computed on this box ...
-    assert np.abs(enc[0] - enc_o.numpy()).max() <= ACT_TOL[p]
-    assert np.abs(ad[0] - ad_o.numpy()).max() <= ACT_TOL[p]
+    _act_close(enc[0], enc_o.numpy(), p, name + " enc vs oracle")
+    _act_close(ad[0], ad_o.numpy(), p, name + " adaptor vs oracle")
     # ... and against the reference's own outputs committed from the build container
     tl, t_valid = meta["cases"][name]["target_len"], Wm.lfr_frames(n_valid)
-    assert np.abs(enc[0] - blobs[f"{name}.enc"]).max() <= ACT_TOL[p]
-    assert np.abs(ad[0, :tl] - blobs[f"{name}.adaptor"]).max() <= ACT_TOL[p]
+    _act_close(enc[0], blobs[f"{name}.enc"], p, name + " enc vs pins")
+    _act_close(ad[0, :tl], blobs[f"{name}.adaptor"], p, name + " adaptor vs pins")
+    assert np.array_equal(ids[0], blobs[f"{name}.ids"]), "ids differ from the reference pins"
     # padded rows are exactly zero, as the reference's mask sweeps / length control leave them
     assert not enc[0, t_valid:].any() and not ad[0, tl:].any()
     # ids from the CUDA enc (the real pipeline) vs the oracle's logits on the oracle's enc
@@ -79,8 +82,8 @@ def test_front_end_taps(engine, weights, consts):
     assert np.abs(np.exp(logmel) - np.exp(ref)).max() <= 1e-5 * max(1.0, float(np.exp(ref).max()))
     assert np.abs(logmel - ref).max() <= 5e-3
     assert np.abs(engine.read_tap("lfr") - taps["lfr"].numpy()).max() <= 5e-3
-    for name, tol in (("layer0", 1e-3), ("layer1", 1e-3), ("layer49", 1e-3)):
-        assert np.abs(engine.read_tap(name) - taps[name].numpy()).max() <= tol, name
+    for name in ("layer0", "layer1", "layer49"):
+        _act_close(engine.read_tap(name), taps[name].numpy(), engine.precision, name)
 
 
 @pytest.mark.parametrize("kind", ["structured", "tone", "white", "quiet", "loud"])
@@ -133,8 +136,8 @@ def test_mixed_length_batch_rows_are_independent(engine, weights, consts):
     p = engine.precision
     for b, n in enumerate(lens):
         enc_o, ad_o = O.encode_one(batch[b], n, weights, consts)
-        assert np.abs(enc[b] - enc_o.numpy()).max() <= ACT_TOL[p]
-        assert np.abs(ad[b] - ad_o.numpy()).max() <= ACT_TOL[p]
+        _act_close(enc[b], enc_o.numpy(), p, f"row{b} enc")
+        _act_close(ad[b], ad_o.numpy(), p, f"row{b} adaptor")
         _check_ids(ids[b], O.ctc_logits_one(enc_o, weights), p, f"row{b}")
     # batching does not change a row: row 1 alone gives bit-identical output
     enc1, ad1, ids1 = engine.front_half(batch.numpy()[1:2], lens[1:2])
@@ -269,22 +272,22 @@ def test_sixty_second_segment_full_size(weights, planted_weights, consts, golden
         eng.close()
     info = meta["cases"][name]
     assert enc.shape == (1, 1001, 512) and info["target_len"] == 126
-    assert np.abs(enc[0, ::info["enc_row_stride"]] - blobs[f"{name}.enc_rows"]).max() <= ACT_TOL["bf16x3"]
-    assert np.abs(ad[0, :126][::info["adaptor_row_stride"]] - blobs[f"{name}.adaptor_rows"]).max() <= ACT_TOL["bf16x3"]
+    _act_close(enc[0, ::info["enc_row_stride"]], blobs[f"{name}.enc_rows"], "bf16x3", "sixty enc rows vs pins")
+    _act_close(ad[0, :126][::info["adaptor_row_stride"]], blobs[f"{name}.adaptor_rows"], "bf16x3", "sixty adaptor rows vs pins")
     assert not ad[0, 126:].any()
     strict = int((ids[0] != blobs[f"{name}.ids"]).sum())
     print(f"[sixty/bf16x3] strict id mismatches vs reference pins: {strict}/1001")
-    assert strict <= 10
+    assert strict == 0
     eng = FrontHalf(planted_weights, device=0, max_batch=1, max_samples=n_phys, precision="bf16x3")
     try:
         ids_p = eng.ctc(enc)
     finally:
         eng.close()
     margin = blobs[f"{name}.margin_planted"]
-    clear = margin > MARGIN_TOL["bf16x3"]
     strict = int((ids_p[0] != blobs[f"{name}.ids_planted"]).sum())
-    print(f"[sixty/planted] strict id mismatches vs reference pins: {strict}/1001, distinct ids {len(np.unique(ids_p))}")
-    assert np.array_equal(ids_p[0][clear], blobs[f"{name}.ids_planted"][clear])
+    print(f"[sixty/planted] strict id mismatches vs reference pins: {strict}/1001, distinct ids {len(np.unique(ids_p))}, "
+          f"min margin {margin.min():.2e}")
+    assert strict == 0
 
 
 def test_lookahead_long_file_matches_per_segment_calls(weights):
@@ -308,7 +311,7 @@ def test_lookahead_long_file_matches_per_segment_calls(weights):
     engine.close()
 
 
-def test_config4_full_size_one_hour_file(planted_weights):
+def test_config4_full_size_one_hour_file(planted_weights, consts):
     """BASELINE config 4 at full size: 3600 s of audio cut exactly as core/orchestrator.py:128-136 cuts it
     (60 s windows, 4 s overlap): 65 windows, 64 x 60 s + 1 x 16 s.  The look-ahead path batches the equal-length windows
     (32 per batch: the candidate-list vocabulary path, CTA-pair GEMMs); a sample of windows, including the first, the
@@ -331,19 +334,27 @@ def test_config4_full_size_one_hour_file(planted_weights):
             a, b = windows[k]
             enc, ad, ids = engine.front_half(audio[None, a:b], [b - a])
             r = res[k]
-            # a single window takes the three-product vocabulary projection, a batch of 32 the candidate lists with
-            # fp32 rescoring: the ids may differ on a near-tie (both are inside the parity contract)
-            assert (ids != r.ids).sum() <= 2
+            # a single window takes the three-product vocabulary projection, a batch of 32 the candidate lists; both
+            # decide by the same fp32 rescoring of the columns that can hold the maximum, so the ids are identical
+            assert np.array_equal(ids, r.ids)
             assert np.abs(enc - r.enc_output).max() <= 1e-5 * max(np.abs(enc).max(), 1.0)
             assert np.abs(ad - r.adaptor_output).max() <= 1e-5 * max(np.abs(ad).max(), 1.0)
             assert len(np.unique(r.ids)) > 5                        # the planted projection makes the ids vary
         # neighbouring windows overlap by 4 s of audio but are independent computations: nothing is shared or reused
         assert not np.array_equal(res[0].ids, res[1].ids)
+        # sampled windows (first, one from the second batch, the short tail) against the oracle
+        for k in (0, 40, 64):
+            a, b = windows[k]
+            seg = torch.from_numpy(audio[a:b])
+            enc_o, ad_o = O.encode_one(seg, b - a, planted_weights, consts)
+            _act_close(res[k].enc_output[0], enc_o.numpy(), "bf16x3", f"config4 window {k} enc")
+            _act_close(res[k].adaptor_output[0], ad_o.numpy(), "bf16x3", f"config4 window {k} adaptor")
+            _check_ids(res[k].ids[0], O.ctc_logits_one(enc_o, planted_weights), "bf16x3", f"config4 window {k}")
     finally:
         engine.close()
 
 
-def test_config5_full_size_256_segments_in_batches(weights):
+def test_config5_full_size_256_segments_in_batches(weights, consts):
     """BASELINE config 5 at full size: 256 x 60 s segments through a context of 32 (8 internal batches).
     The 256 segments are 32 distinct signals repeated 8 times, so every repeat must reproduce the first batch bit for
     bit (a batch's result may not depend on what ran before it, nor on its position in the call), and the launch
@@ -364,6 +375,11 @@ def test_config5_full_size_256_segments_in_batches(weights):
         for rep in range(8):
             assert np.array_equal(ids[32 * rep:32 * rep + 32], ids1)
             assert np.array_equal(enc[32 * rep:32 * rep + 32], enc1)
+        # sampled segments of different internal batches against the oracle
+        for k in (5, 100, 255):
+            enc_o, _ = O.encode_one(torch.from_numpy(big[k]), s, weights, consts)
+            _act_close(enc[k], enc_o.numpy(), "bf16x3", f"config5 segment {k} enc")
+            _check_ids(ids[k], O.ctc_logits_one(enc_o, weights), "bf16x3", f"config5 segment {k}")
     finally:
         engine.close()
 
@@ -391,7 +407,56 @@ def test_config3_full_size_mixed_length_batch(weights, planted_weights, consts):
     shortest, longest = int(np.argmin(lens)), int(np.argmax(lens))
     for b in (shortest, longest):
         enc_o, ad_o = O.encode_one(batch[b], lens[b], planted_weights, consts)
-        assert np.abs(enc[b] - enc_o.numpy()).max() <= ACT_TOL["bf16x3"]
-        assert np.abs(ad[b] - ad_o.numpy()).max() <= ACT_TOL["bf16x3"]
+        _act_close(enc[b], enc_o.numpy(), "bf16x3", f"config3 row{b} enc")
+        _act_close(ad[b], ad_o.numpy(), "bf16x3", f"config3 row{b} adaptor")
         _check_ids(ids[b], O.ctc_logits_one(enc_o, planted_weights), "bf16x3", f"config3 row{b}")
     eng.close()
+
+
+def test_benchmarked_batch_all_rows_match_oracle_and_reference_pins(weights, planted_weights, consts):
+    """The configuration every headline number is quoted on (BASELINE configs[1]; bench.py's first input set on rank 0:
+    32 x 60 s of white noise, seeds 1234 + i) through fa_front_half in bf16x3 — CTA-pair GEMMs, candidate-list vocabulary
+    path, fast-mode attention.  ALL 32 rows: enc / adaptor against the oracle within ACT_TOL, ids identical to the oracle
+    and to the pins tests/golden/make_golden.py --bench32 took from the reference's own model_definition.py; the same
+    with the planted CTC projection, whose ids vary every few frames."""
+    import json
+    import os
+    from fun_asr_gguf_b200 import synth
+    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    pins = np.load(os.path.join(d, "bench32_outputs.npz"))
+    info = json.load(open(os.path.join(d, "bench32_outputs.json")))
+    s = 60 * SR
+    batch = torch.stack([synth.white(s, i) for i in range(32)])
+    eng = FrontHalf(weights, device=0, max_batch=32, max_samples=s, precision="bf16x3")
+    try:
+        enc, ad, ids = eng.front_half(batch.numpy(), [s] * 32)
+    finally:
+        eng.close()
+    from tests import planted
+    got = {}
+    for key, wts in (("ids_planted", planted_weights),
+                     ("ids_planted_white", planted.plant(weights, consts, cal=synth.white(6 * SR, 9999)))):
+        eng = FrontHalf(wts, device=0, max_batch=32, max_samples=s, precision="bf16x3")
+        try:
+            got[key] = eng.ctc(enc)
+        finally:
+            eng.close()
+    for key, g in (("ids", ids), ("ids_planted", got["ids_planted"]), ("ids_planted_white", got["ids_planted_white"])):
+        bad = g != pins[key]
+        margin = pins[key.replace("ids", "margin")]
+        print(f"[bench32/{key}] strict id mismatches vs reference pins {int(bad.sum())}/{g.size}; distinct ids {len(np.unique(g))}; "
+              f"min top-2 margin {margin.min():.2e}" + (f"; margins at the mismatches {np.sort(margin[bad])[:8]}" if bad.any() else ""))
+    for key, g in (("ids", ids), ("ids_planted", got["ids_planted"]), ("ids_planted_white", got["ids_planted_white"])):
+        assert np.array_equal(g, pins[key]), f"{key}: {int((g != pins[key]).sum())} ids differ from the reference pins"
+    _act_close(enc[:, ::info["enc_row_stride"]], pins["enc_rows"], "bf16x3", "bench32 enc rows vs pins")
+    _act_close(ad[:, :126][:, ::info["adaptor_row_stride"]], pins["adaptor_rows"], "bf16x3", "bench32 adaptor rows vs pins")
+    worst_e = worst_a = 0.0
+    for b in range(32):
+        enc_o, ad_o = O.encode_one(batch[b], s, weights, consts)
+        worst_e = max(worst_e, float(np.abs(enc[b] - enc_o.numpy()).max()))
+        worst_a = max(worst_a, float(np.abs(ad[b] - ad_o.numpy()).max()))
+        lg = O.ctc_logits_one(enc_o, weights)
+        assert np.array_equal(ids[b], lg.argmax(-1).numpy()), f"row {b}: ids differ from the oracle"
+        assert not ad[b, 126:].any()
+    print(f"[bench32] all 32 rows vs oracle: enc max|d| {worst_e:.3e}, adaptor max|d| {worst_a:.3e}")
+    assert worst_e <= ACT_TOL["bf16x3"] and worst_a <= ACT_TOL["bf16x3"]

@@ -211,3 +211,50 @@ def test_checkpoint_key_mapping_follows_load_weights(weights, monkeypatch):
     monkeypatch.setattr(torch, "load", lambda path, map_location=None: bad)
     with pytest.raises(ValueError):
         Wm.load_checkpoint("model.pt")
+
+
+def test_sessions_survive_an_engine_rebuild(monkeypatch):
+    """a segment longer than FUNASR_B200_MAX_SECONDS replaces the shared engine.  Sessions resolve the engine
+    on every run, the old engine is closed only after the new one exists, the capacity is rounded up to whole seconds so
+    the CTC session's request does not force a second rebuild, and the checkpoint tensors are not re-read."""
+    from fun_asr_gguf_b200 import engine as E
+    built, loads = [], []
+
+    class FakeFrontHalf:
+        def __init__(self, tensors, device=0, max_batch=4, max_samples=0, precision="bf16x3"):
+            self.max_samples, self.max_batch, self.closed = max_samples, max_batch, False
+            built.append(self)
+
+        def close(self):
+            self.closed = True
+
+        @staticmethod
+        def frames(s):
+            return Wm.lfr_frames(s)
+
+        def encode(self, audio, ilens):
+            assert not self.closed and audio.shape[1] <= self.max_samples
+            b, t = audio.shape[0], Wm.lfr_frames(audio.shape[1])
+            return np.zeros((b, t, 512), np.float32), np.zeros((b, t, 1024), np.float32)
+
+        def ctc(self, enc):
+            assert not self.closed and enc.shape[1] <= Wm.lfr_frames(self.max_samples)
+            return np.zeros(enc.shape[:2], np.int32)
+
+    monkeypatch.setattr(E, "FrontHalf", FakeFrontHalf)
+    monkeypatch.setattr(Wm, "random_weights", lambda seed: loads.append(seed) or {})
+    monkeypatch.setattr(ort_shim, "_engines", {})
+    monkeypatch.setattr(ort_shim, "_tensors", {})
+    monkeypatch.delenv("FUNASR_B200_MAX_SECONDS", raising=False)
+    enc = ort_shim.InferenceSession("m/Fun-ASR-Nano-Encoder-Adaptor.fp32.onnx")
+    ctc = ort_shim.InferenceSession("m/Fun-ASR-Nano-CTC.fp32.onnx")
+    assert len(built) == 1 and built[0].max_samples == 62 * 16000
+    s = int(63.4 * 16000) + 7
+    e, _ = enc.run(None, {"audio": np.zeros((1, 1, s), np.float32), "ilens": np.array([s], np.int64)})
+    assert len(built) == 2 and built[0].closed and not built[1].closed and built[1].max_samples == 64 * 16000
+    ctc.run(None, {"enc_output": e})                       # same engine: no second rebuild, and not the closed one
+    assert len(built) == 2 and loads == [0]
+    enc.run(None, {"audio": np.zeros((1, 1, 16000), np.float32)})
+    assert len(built) == 2
+    for t in (1, 17, 1001, 1034):
+        assert Wm.lfr_frames(ort_shim.samples_for_frames(t)) == t and (t == 1 or Wm.lfr_frames(ort_shim.samples_for_frames(t) - 1) == t - 1)

@@ -1,6 +1,7 @@
 """The oracle against its pins (CPU).  Pins = outputs of the reference's own
 model_definition.py (see tests/golden/make_golden.py); the reference ships none of its own."""
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -135,3 +136,18 @@ def test_oracle_vs_live_reference(weights, consts):
     assert torch.equal(mel_ref, consts["const.mel_fbank"])
     assert torch.equal(ref.stft.cos_kernel[:, 0], consts["const.dft_cos"])
     assert torch.equal(ref.stft.sin_kernel[:, 0], consts["const.dft_sin"])
+
+
+def test_oracle_reproduces_the_benchmark_batch_pins(weights, consts):
+    """Row 3 of the 32 x 60 s batch bench.py measures on (make_golden.py --bench32): the oracle gives the ids and the
+    sampled enc / adaptor rows the reference's own model_definition.py gave."""
+    import json
+    from fun_asr_gguf_b200 import synth
+    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    pins = np.load(os.path.join(d, "bench32_outputs.npz"))
+    info = json.load(open(os.path.join(d, "bench32_outputs.json")))
+    a = synth.white(60 * 16000, 3)
+    enc, ad = O.encode_one(a, a.shape[0], weights, consts)
+    assert np.array_equal(O.ctc_ids_one(enc, weights).numpy(), pins["ids"][3])
+    assert np.abs(enc[::info["enc_row_stride"]].numpy() - pins["enc_rows"][3]).max() <= 1e-6
+    assert np.abs(ad[:126:info["adaptor_row_stride"]].numpy() - pins["adaptor_rows"][3]).max() <= 1e-6

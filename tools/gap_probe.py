@@ -6,7 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 from fun_asr_gguf_b200 import FrontHalf, weights as Wm
-from tests import signals
+from fun_asr_gguf_b200 import synth as signals
 
 B, S = 32, 960000
 dev = torch.device("cuda", 0)

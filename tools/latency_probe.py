@@ -13,7 +13,7 @@ sys.path.insert(0, ROOT)
 import numpy as np
 
 from fun_asr_gguf_b200 import FrontHalf, weights as Wm
-from tests import signals
+from fun_asr_gguf_b200 import synth as signals
 
 S = 960000
 w = Wm.random_weights(0)
