@@ -280,6 +280,10 @@ def run_ours(args) -> None:
     plans = make_plan(args, world, rank)
     P0 = plans[0]
     eng = FrontHalf(Wm.random_weights(0), device=local, max_batch=P0.max_batch, max_samples=P0.max_samples, precision=args.precision)
+    # everything below runs on one non-default torch stream: the engine launches on it, torch's events time it, and
+    # (unlike the legacy default stream) it can be captured, so short batches replay as CUDA graphs as in production
+    work_stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(work_stream)
     eng.use_torch_stream()
 
     # device-resident inputs and outputs for `value`

@@ -108,6 +108,12 @@ struct AttnParams {
     __nv_bfloat16* ctx_lo;
     int ldo;
     int force_exact;                           // FUNASR_B200_ATTENTION_SHIFT=exact: every item in the exact (two-pass) mode
+    int items;                                 // (segment, head, query tile) items of the launch
+    // packed rows (kernels.h Packing; all null for the uniform [batch][frames] layout): segment b is rows
+    // seg_off[b] .. seg_off[b] + kv_len[b] - 1, items are dealt over the segments in `order` (longest first)
+    const int* seg_off;
+    const int* order;
+    const int* tile_off;
     long long* dbg;                            // tuning aid (FUNASR_B200_ATTN_TIMING): cycles the MMA warp waits, by cause
 };
 
@@ -137,7 +143,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, const __grid_constant
 
     const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     const int q_tiles = (p.frames + QT - 1) / QT;
-    const int items = p.batch * p.heads * q_tiles;
+    const int items = p.items;
 
     if (threadIdx.x < kRedoWords) redo_bits[threadIdx.x] = 0u;
     if (threadIdx.x == 0) {
@@ -161,13 +167,31 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, const __grid_constant
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_ptr, 0);    // provably warp-uniform
     grid_dependency_wait();                       // everything above overlapped the previous kernel's tail
 
-    // item -> (segment b, head h, query tile qt); key tiles n
-    auto decode = [&](int item, int& b, int& h, int& qt, int& n, int& klen) {
-        qt = item % q_tiles;
-        const int bh = item / q_tiles;
-        h = bh % p.heads;
-        b = bh / p.heads;
-        klen = p.kv_len ? p.kv_len[b] : p.frames;
+    // item -> (segment b, head h, query tile qt); key tiles n; first row of the segment and its query count
+    auto decode = [&](int item, int& b, int& h, int& qt, int& n, int& klen, int& row0, int& qlen) {
+        if (p.seg_off) {
+            // packed: the items of the k-th longest segment start at heads * tile_off[k]
+            int lo = 0, hi = p.batch;                        // invariant: tile_off[lo] * heads <= item < tile_off[hi] * heads
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (p.tile_off[mid] * p.heads <= item) lo = mid; else hi = mid;
+            }
+            const int t0 = p.tile_off[lo], qtk = p.tile_off[lo + 1] - t0, local = item - t0 * p.heads;
+            h = local / qtk;
+            qt = local - h * qtk;
+            b = p.order[lo];
+            klen = p.kv_len[b];
+            qlen = klen;
+            row0 = p.seg_off[b];
+        } else {
+            qt = item % q_tiles;
+            const int bh = item / q_tiles;
+            h = bh % p.heads;
+            b = bh / p.heads;
+            klen = p.kv_len ? p.kv_len[b] : p.frames;
+            qlen = p.frames;
+            row0 = b * p.frames;
+        }
         n = (klen + KT - 1) / KT;
     };
 
@@ -214,9 +238,8 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, const __grid_constant
             ++cnt;
         };
         FA_ATT_SEQUENCE_BEGIN
-            int b, h, qt, n, klen;
-            decode(item, b, h, qt, n, klen);
-            const int row0 = b * p.frames;
+            int b, h, qt, n, klen, row0, qlen;
+            decode(item, b, h, qt, n, klen, row0, qlen);
             if (exact)
                 for (int j = 0; j < n; ++j) load_plane(1, 0, h, row0 + j * KT);                // pass 1: K hi
             for (int j = 0; j < 2 && j < n; ++j) {                                             // pass 2: K0, K1, then V(j), K(j+2)
@@ -277,8 +300,8 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, const __grid_constant
                           ks ? 1u : first_accum);
         };
         FA_ATT_SEQUENCE_BEGIN
-            int b, h, qt, n, klen;
-            decode(item, b, h, qt, n, klen);
+            int b, h, qt, n, klen, row0, qlen;
+            decode(item, b, h, qt, n, klen, row0, qlen);
             trace(item_it, 0);
             twait(0, bar_qfull, item_it & 1);
             trace(item_it, 1);                       // this item's Q (hi plane) is in TMEM
@@ -432,8 +455,8 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, const __grid_constant
             return mx;
         };
         FA_ATT_SEQUENCE_BEGIN
-            int b, h, qt, n, klen;
-            decode(item, b, h, qt, n, klen);
+            int b, h, qt, n, klen, row0, qlen;
+            decode(item, b, h, qt, n, klen, row0, qlen);
             float mx = -INFINITY;
             float* mxb = mx_smem + (item_it & 1) * 4 * QT;           // buffers alternate by item parity
             if (warp == 2) trace(item_it, 16);
@@ -519,11 +542,11 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, const __grid_constant
         // pass 1 can start; the lo plane, which pass 2 needs some thousand cycles later, follows.
         constexpr int kQW = DK / 2;                                 // 32-bit words per row per plane
         auto q_src = [&](int item, int pl, bool& ok) -> const uint4* {
-            int b, h, qt, n, klen;
-            decode(item, b, h, qt, n, klen);
+            int b, h, qt, n, klen, row0, qlen;
+            decode(item, b, h, qt, n, klen, row0, qlen);
             const int row = qt * QT + r;
-            ok = row < p.frames;
-            const int64_t off = ((int64_t)b * p.frames + row) * p.ld + h * DK;
+            ok = row < qlen;
+            const int64_t off = ((int64_t)row0 + row) * p.ld + h * DK;
             return reinterpret_cast<const uint4*>((pl ? p.q_lo : p.q_hi) + off);
         };
         auto q_fetch = [&](int item, int pl, uint32_t (&w)[kQW]) {
@@ -563,8 +586,8 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, const __grid_constant
             q_fetch(item, 1, qw);
             q_store(1, qw, bar_qlofull);
             while (item < items) {
-            int b, h, qt, n, klen;
-            decode(item, b, h, qt, n, klen);
+            int b, h, qt, n, klen, seg_row0, qlen;
+            decode(item, b, h, qt, n, klen, seg_row0, qlen);
             int next = item, next_k = k;
             advance(next, next_k);
             if (next < items) {
@@ -591,12 +614,12 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, const __grid_constant
             if (!exact && __any_sync(0xffffffffu, !(l_row <= 0x1p60f)) && lane == 0)
                 atomicOr(const_cast<uint32_t*>(redo_bits) + (k >> 5), 1u << (k & 31));
             const int row = qt * QT + r;
-            const int64_t grow = (int64_t)b * p.frames + row;
+            const int64_t grow = (int64_t)seg_row0 + row;
             // O leaves TMEM 64 columns at a time; the accumulator is handed back to the MMA warp as soon as the last
             // columns are in registers, before they are scaled, split and stored (the next item's first P V is only
             // some three thousand cycles behind this item's last one)
             auto emit = [&](const uint32_t (&o)[32], int c) {
-                if (row >= p.frames) return;
+                if (row >= qlen) return;
                 const int64_t off = grow * p.ldo + h * DK + c * 32;
                 if (p.ctx) {
 #pragma unroll
@@ -627,6 +650,10 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, const __grid_constant
                 // hand-back for ~6 k cycles of every item.
                 unsigned char* stg = smem_raw + (stage_base - raw) + (warp - 18) * 16384;
                 const uint32_t stg_u32 = stage_base + (warp - 18) * 16384;
+                // packed rows: the store map cannot clip at the end of a segment (the next segment's rows follow), so a
+                // warp whose 32 rows straddle the end writes its valid rows with plain stores (once per segment and head)
+                const int wrow0 = qt * QT + quarter * 32;
+                const bool direct = p.seg_off != nullptr && wrow0 + 32 > qlen;
                 if (lane == 0) bulk_wait_read0();                    // the previous item's stores have read the tiles (an item ago)
                 __syncwarp();
 #pragma unroll 1
@@ -644,6 +671,18 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, const __grid_constant
 #pragma unroll
                     for (int i = 0; i < 16; ++i)
                         split_bf16x2(__uint_as_float(o[2 * i]) * inv, __uint_as_float(o[2 * i + 1]) * inv, hw[i], lw[i]);
+                    if (direct) {
+                        if (row < qlen) {
+                            const int64_t off = grow * p.ldo + h * DK + c * 32;
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                reinterpret_cast<uint4*>(p.ctx_hi + off)[i] = make_uint4(hw[4 * i], hw[4 * i + 1], hw[4 * i + 2], hw[4 * i + 3]);
+                                if (p.ctx_lo)
+                                    reinterpret_cast<uint4*>(p.ctx_lo + off)[i] = make_uint4(lw[4 * i], lw[4 * i + 1], lw[4 * i + 2], lw[4 * i + 3]);
+                            }
+                        }
+                        continue;
+                    }
                     unsigned char* box = stg + (c >> 1) * 8192;          // hi tile, then lo tile, of this 64-column box
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
@@ -654,12 +693,12 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, const __grid_constant
                 }
                 fence_async_smem();
                 __syncwarp();
-                const int row0 = qt * QT + quarter * 32;
-                if (lane == 0 && row0 < p.frames) {                  // rows past the segment's end are clipped by the map
+                if (lane == 0 && !direct && wrow0 < qlen) {          // uniform layout: rows past the segment's end are clipped by the map
+                    const int mrow = p.seg_off ? seg_row0 + wrow0 : wrow0, mseg = p.seg_off ? 0 : b;
 #pragma unroll
                     for (int bx = 0; bx < DK / 64; ++bx) {
-                        tma_store_4d(&map_out, stg_u32 + bx * 8192, h * DK + bx * 64, row0, b, 0);
-                        if (p.ctx_lo) tma_store_4d(&map_out, stg_u32 + bx * 8192 + 4096, h * DK + bx * 64, row0, b, 1);
+                        tma_store_4d(&map_out, stg_u32 + bx * 8192, h * DK + bx * 64, mrow, mseg, 0);
+                        if (p.ctx_lo) tma_store_4d(&map_out, stg_u32 + bx * 8192 + 4096, h * DK + bx * 64, mrow, mseg, 1);
                     }
                     bulk_commit();
                 }
@@ -744,12 +783,13 @@ void attention_tc_init_device() {
 }
 
 void launch_attention_tc(Planes qkv, int64_t plane_stride, int ld, int d_model, int batch, int frames, int heads, int dk,
-                         const int* kv_len, float* ctx_f32, Planes ctx_pl, int ldo, cudaStream_t st) {
+                         const int* kv_len, float* ctx_f32, Planes ctx_pl, int ldo, cudaStream_t st, const Packing* pk) {
     FA_REQUIRE(dk == 64 || dk == 128, "attention head width must be 64 or 128");
+    FA_REQUIRE(!pk || kv_len, "packed attention needs the per-segment lengths");
     FA_REQUIRE(heads * dk == d_model, "heads * d_k must equal the model width");
     FA_REQUIRE(ldo % 8 == 0 && ld % 8 == 0, "attention strides must be multiples of 8");
     FA_REQUIRE(qkv.lo == qkv.hi + plane_stride, "attention expects the lo plane `plane_stride` elements after the hi plane");
-    const int rows = batch * frames;
+    const int rows = pk ? pk->total_rows : batch * frames;        // rows past the end are zero-filled by the load map
     const TcOperand mkv = tc_make_operand(qkv.hi, rows, ld, ld, plane_stride, 2, KT);     // 128-row boxes of k and v
     AttnParams p{};
     p.batch = batch; p.frames = frames; p.heads = heads; p.d_model = d_model; p.ld = ld; p.kv_len = kv_len;
@@ -761,8 +801,10 @@ void launch_attention_tc(Planes qkv, int64_t plane_stride, int ld, int d_model, 
     }
     CUtensorMap map_out;
     memset(&map_out, 0, sizeof(map_out));
-    if (ctx_pl.hi && !ctx_f32) map_out = att_out_map(ctx_pl, ldo, d_model, frames, batch);
-    const int items = batch * heads * cdiv(frames, QT);
+    if (ctx_pl.hi && !ctx_f32) map_out = pk ? att_out_map(ctx_pl, ldo, d_model, pk->total_rows, 1) : att_out_map(ctx_pl, ldo, d_model, frames, batch);
+    const int items = pk ? heads * pk->total_tiles : batch * heads * cdiv(frames, QT);
+    p.items = items;
+    if (pk) { p.seg_off = pk->seg_off; p.order = pk->order; p.tile_off = pk->tile_off; }
     int grid = items < g_att_sms ? items : g_att_sms;
     if (const char* e = getenv("FUNASR_B200_ATT_SMS")) { const int v = atoi(e); if (v > 0 && v < grid) grid = v; }   // tuning aid: fewer CTAs
     // the repeat bitmap holds one bit per item of a CTA's sequence; more would spill into the barriers behind it
@@ -774,7 +816,7 @@ void launch_attention_tc(Planes qkv, int64_t plane_stride, int ld, int d_model, 
         FA_CUDA(cudaMemsetAsync(dbg, 0, (size_t)grid * 16 * sizeof(long long), st));
         p.dbg = dbg;
     }
-    prof_note_work(4.0 * batch * heads * (double)frames * frames * dk, 0.0);
+    prof_note_work(pk ? 4.0 * heads * pk->sum_len_sq * dk : 4.0 * batch * heads * (double)frames * frames * dk, 0.0);
     if (g_prof_on) prof_note_tag(dk == 128 ? "dk128" : "dk64");
     if (dk == 128) {
         FA_LAUNCH(k_attention_tc<128>, grid, kAttThreads, ACfg<128>::kSmemBytes, st, mkv.map, map_out, p);

@@ -144,6 +144,8 @@ void Context::set_stream(cudaStream_t s) {
     if (own_stream_ && stream_) cudaStreamDestroy(stream_);
     stream_ = s;
     own_stream_ = false;
+    // the legacy default stream (and the per-thread one) cannot be captured: calls on it launch eagerly
+    capturable_ = s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread;
 }
 
 void Context::load_tensor(const std::string& name, const float* host, const std::vector<int64_t>& shape) {
@@ -364,11 +366,13 @@ void Context::finalize() {
         logits_rows_ = (int)std::min<size_t>(M, 2048);
         logits_.alloc((size_t)logits_rows_ * vocab_ * 4);
     }
-    lens_.alloc((size_t)3 * max_batch_ * sizeof(int));
+    len_ints_ = 6 * max_batch_ + 2;              // n_valid, t_valid, target_len, seg_off[B+1], order[B], tile_off[B+1]
+    lens_.alloc((size_t)len_ints_ * sizeof(int));
     d_nvalid_ = lens_.as<int>();
     d_tvalid_ = d_nvalid_ + max_batch_;
     d_tlen_ = d_tvalid_ + max_batch_;
-    FA_CUDA(cudaMallocHost(&h_lens_, (size_t)kLenSlots * 3 * max_batch_ * sizeof(int)));
+    FA_CUDA(cudaMallocHost(&h_lens_, (size_t)kLenSlots * len_ints_ * sizeof(int)));
+    if (const char* pe = getenv("FUNASR_B200_PACKED")) allow_packed_env_ = !(pe[0] == '0');     // comparison aid
     FA_CUDA(cudaStreamSynchronize(stream_));
     finalized_ = true;
 }
@@ -411,14 +415,15 @@ void Context::linear(const Act& a, const Linear& w, int m, const Epilogue& ep_in
 }
 
 void Context::attention(const float* qkv, int ld, int d_model, int batch, int frames, int heads, const int* kv_len,
-                        float* ctx_f32, Planes ctx_pl, int ldo) {
+                        float* ctx_f32, Planes ctx_pl, int ldo, const Packing* pk) {
     if (simt_attention_) {
+        FA_REQUIRE(pk == nullptr, "the CUDA-core attention runs on the uniform layout only");
         launch_attention_simt(qkv, qkv + d_model, qkv + 2 * d_model, ld, batch, frames, heads, d_model / heads, kv_len,
                               ctx_f32, ctx_pl, ldo, stream_);
     } else {
         const Planes pl = qkv_planes();
         launch_attention_tc(pl, pl.lo - pl.hi, ld, d_model, batch, frames, heads, d_model / heads, kv_len, ctx_f32, ctx_pl,
-                            ldo, stream_);
+                            ldo, stream_, pk);
     }
 }
 
@@ -474,7 +479,7 @@ void Context::ensure_room(int batch, int64_t s_phys) const {
 // ------------------------------------------------------------------------------------ layers
 
 void Context::sanm_layer(const SanmLayer& L, bool first, int batch, int frames) {
-    const int M = batch * frames;
+    const int M = enc_rows(batch, frames);
     const bool f32 = prec_ == kFp32;
     float* x = x_.as<float>();
     const float* xin = first ? x0_.as<float>() : x;
@@ -484,10 +489,10 @@ void Context::sanm_layer(const SanmLayer& L, bool first, int batch, int frames) 
     linear(h, L.qkv, M, qkv_epilogue(kDenc, 4, true));      // fp32 v feeds the FSMN branch
     const float* qkv = qkv_.as<float>();
     // x <- (x) + fsmn(v*m): the memory branch plus, except in layer 0, the block's residual
-    launch_fsmn(qkv + 2 * kDenc, 3 * kDenc, L.fsmn_w, d_tvalid_, batch, frames, first ? nullptr : x, x, stream_);
+    launch_fsmn(qkv + 2 * kDenc, 3 * kDenc, L.fsmn_w, d_tvalid_, batch, frames, first ? nullptr : x, x, stream_, packing());
     const Act c = ctx_act(kDenc);
     attention(qkv, 3 * kDenc, kDenc, batch, frames, 4, d_tvalid_, f32 ? const_cast<float*>(c.f32) : nullptr,
-              f32 ? Planes{} : c.pl, kDenc);
+              f32 ? Planes{} : c.pl, kDenc, packing());
     Epilogue eo;
     eo.resid = x; eo.ldr = kDenc; eo.out_f32 = x; eo.ldc = kDenc;
     linear(c, L.out, M, eo);
@@ -504,8 +509,9 @@ void Context::sanm_layer(const SanmLayer& L, bool first, int batch, int frames) 
     linear(f, L.w2, M, e2);
 }
 
-void Context::projector(const Projector& P, const Act& in, int batch, int frames, const int* kv_len) {
-    const int M = batch * frames, d = P.d;
+void Context::projector(const Projector& P, const Act& in, int batch, int frames, const int* kv_len, bool packed) {
+    const int M = packed ? pk_.total_rows : batch * frames, d = P.d;
+    const Packing* pk = packed ? &pk_ : nullptr;
     const bool f32 = prec_ == kFp32;
     float* x = x_.as<float>();
     const Act f = ffn_act(kDffn);
@@ -522,7 +528,7 @@ void Context::projector(const Projector& P, const Act& in, int batch, int frames
         linear(h, B.qkv, M, qkv_epilogue(d, P.heads, false));
         const Act c = ctx_act(d);
         attention(qkv_.as<float>(), 3 * d, d, batch, frames, P.heads, kv_len, f32 ? const_cast<float*>(c.f32) : nullptr,
-                  f32 ? Planes{} : c.pl, d);
+                  f32 ? Planes{} : c.pl, d, pk);
         Epilogue eo;
         eo.resid = x; eo.ldr = d; eo.out_f32 = x; eo.ldc = d;
         linear(c, B.out, M, eo);
@@ -540,19 +546,46 @@ void Context::projector(const Projector& P, const Act& in, int batch, int frames
 
 // ------------------------------------------------------------------------------------ graphs
 
-void Context::stage_lengths(int batch, int64_t s_phys, const int64_t* h_ilens) {
+void Context::stage_lengths(int batch, int64_t s_phys, const int64_t* h_ilens, bool allow_packed) {
     const int slot = len_next_;
     len_next_ = (len_next_ + 1) % kLenSlots;
     FA_CUDA(cudaEventSynchronize(len_ev_[slot]));
-    int* hl = h_lens_ + (size_t)slot * 3 * max_batch_;
+    int* hl = h_lens_ + (size_t)slot * len_ints_;
+    int* h_tv = hl + max_batch_;
+    int* h_off = hl + 3 * max_batch_;            // [B+1]
+    int* h_order = h_off + max_batch_ + 1;       // [B]
+    int* h_tile = h_order + max_batch_;          // [B+1]
+    const int frames = lfr_frames_of(s_phys);
+    int total = 0, longest = 0;
+    double sq = 0.0;
     for (int b = 0; b < batch; ++b) {
         const int64_t nv = h_ilens[b];
         FA_REQUIRE(nv >= 1 && nv <= s_phys, "ilens must satisfy 1 <= ilens[b] <= samples");
         hl[b] = (int)nv;
-        hl[max_batch_ + b] = lfr_frames_of(nv);
+        h_tv[b] = lfr_frames_of(nv);
         hl[2 * max_batch_ + b] = target_len_of(nv);
+        h_off[b] = total;
+        total += h_tv[b];
+        longest = std::max(longest, h_tv[b]);
+        sq += (double)h_tv[b] * h_tv[b];
+        h_order[b] = b;
     }
-    FA_CUDA(cudaMemcpyAsync(lens_.p, hl, (size_t)3 * max_batch_ * sizeof(int), cudaMemcpyHostToDevice, stream_));
+    h_off[batch] = total;
+    // Packed execution only pays (and only differs) when the batch holds padded frames
+    packed_ = allow_packed && allow_packed_env_ && prec_ != kFp32 && !simt_attention_ && !taps_on_ && total < batch * frames;
+    if (packed_) {
+        // attention items are dealt round-robin over the CTAs: longest segments first, so that every CTA's share
+        // mixes long and short items (the cost of an item is proportional to its segment's length)
+        std::stable_sort(h_order, h_order + batch, [&](int a, int b) { return h_tv[a] > h_tv[b]; });
+        int tiles = 0;
+        for (int k = 0; k < batch; ++k) { h_tile[k] = tiles; tiles += cdiv(h_tv[h_order[k]], 128); }
+        h_tile[batch] = tiles;
+        pk_.seg_off = d_nvalid_ + 3 * max_batch_;
+        pk_.order = pk_.seg_off + max_batch_ + 1;
+        pk_.tile_off = pk_.order + max_batch_;
+        pk_.total_rows = total; pk_.total_tiles = tiles; pk_.max_len = longest; pk_.sum_len_sq = sq;
+    }
+    FA_CUDA(cudaMemcpyAsync(lens_.p, hl, (size_t)len_ints_ * sizeof(int), cudaMemcpyHostToDevice, stream_));
     FA_CUDA(cudaEventRecord(len_ev_[slot], stream_));
 }
 
@@ -574,43 +607,56 @@ void Context::encode_dev(const float* d_audio, int batch, int64_t s_phys, const 
                          float* d_adaptor) {
     ensure_room(batch, s_phys);
     set_device();
-    stage_lengths(batch, s_phys, h_ilens);
+    stage_lengths(batch, s_phys, h_ilens, true);
     front_end(d_audio, 0, batch, s_phys);
     encoder_graph(batch, s_phys, d_enc, d_adaptor);
 }
 
 // a3 onwards: LFR + position -> 70 SAN-M layers -> enc ; adaptor -> adaptor_output
 void Context::encoder_graph(int batch, int64_t s_phys, float* d_enc, float* d_adaptor, bool record_events) {
-    const int t_mel = (int)(s_phys / kHop + 1), frames = lfr_frames_of(s_phys), M = batch * frames;
+    const int t_mel = (int)(s_phys / kHop + 1), frames = lfr_frames_of(s_phys);
+    const int M = enc_rows(batch, frames);                  // packed: valid frames only
+    const Packing* pk = packing();
+    const int* seg_off = pk ? pk->seg_off : nullptr;
     tap("logmel", logmel_.as<float>(), (int64_t)batch * t_mel, kMels);
     float* lfr_raw = taps_on_ ? adaptor_out_.as<float>() : nullptr;     // borrowed scratch for the tap
-    launch_lfr_embed(logmel_.as<float>(), batch, t_mel, frames, d_nvalid_, pos_enc_, x0_.as<float>(), lfr_raw, stream_);
+    launch_lfr_embed(logmel_.as<float>(), batch, t_mel, frames, d_nvalid_, pos_enc_, x0_.as<float>(), lfr_raw, stream_, seg_off);
     if (lfr_raw) tap("lfr", lfr_raw, M, kDin);
 
+    // the mask sweeps of model_definition.py:210,213 zero the padded frames; packed rows have none
+    const int* sweep = pk ? nullptr : d_tvalid_;
     float* x = x_.as<float>();
     for (int i = 0; i < kEncLayers; ++i) {
         sanm_layer(enc_layers_[i], i == 0, batch, frames);
         if (i == 0) tap("layer0", x, M, kDenc);
         if (i == 1) tap("layer1", x, M, kDenc);
         if (i == 49) {
-            launch_layernorm(x, M, kDenc, after_g_, after_b_, 1e-5f, d_tvalid_, frames, x, Planes{}, stream_);
+            launch_layernorm(x, M, kDenc, after_g_, after_b_, 1e-5f, sweep, frames, x, Planes{}, stream_);
             tap("layer49", x, M, kDenc);
         }
     }
     const bool f32 = prec_ == kFp32;
     Planes encpl;
     if (!f32) encpl = Planes{encpl_.as<__nv_bfloat16>(), encpl_.as<__nv_bfloat16>() + m_max_ * kDenc};
-    launch_layernorm(x, M, kDenc, tp_g_, tp_b_, 1e-5f, d_tvalid_, frames, d_enc, encpl, stream_);
+    Act in; in.f32 = d_enc; in.pl = encpl; in.ld = kDenc;
+    if (pk) {
+        // enc_output leaves in the reference's physical [batch][frames] shape, padded frames zero (the CTC head runs on
+        // it as it is: unmasked, every physical frame — F7); the adaptor goes on with the packed rows
+        launch_layernorm(x, batch * frames, kDenc, tp_g_, tp_b_, 1e-5f, d_tvalid_, frames, d_enc, encpl, stream_, seg_off);
+        in.pl = h_act(kDenc).pl;
+        launch_layernorm(x, M, kDenc, tp_g_, tp_b_, 1e-5f, nullptr, frames, nullptr, in.pl, stream_);
+    } else {
+        launch_layernorm(x, M, kDenc, tp_g_, tp_b_, 1e-5f, d_tvalid_, frames, d_enc, encpl, stream_);
+    }
     if (record_events) FA_CUDA(cudaEventRecord(ev_enc_, stream_));       // enc_output is final: a download may start
 
-    Act in; in.f32 = d_enc; in.pl = encpl; in.ld = kDenc;
-    projector(adaptor_, in, batch, frames, d_tvalid_);
-    launch_row_keep(x, d_adaptor, batch, frames, kDllm, d_tlen_, stream_);
+    projector(adaptor_, in, batch, frames, d_tvalid_, pk != nullptr);
+    launch_row_keep(x, d_adaptor, batch, frames, kDllm, d_tlen_, stream_, seg_off);
     if (record_events) FA_CUDA(cudaEventRecord(ev_ad_, stream_));
 }
 
 // ------------------------------------------------------------------------------------ graph replay
-bool Context::use_graph(int batch) const { return batch <= graph_max_batch_ && !g_prof_on && !taps_on_; }
+bool Context::use_graph(int batch) const { return capturable_ && batch <= graph_max_batch_ && !g_prof_on && !taps_on_; }
 
 // Runs `body` (kernel launches on stream_ only, no host synchronisation) as a CUDA graph: captured and instantiated
 // the first time a (kind, batch, size) is seen, replayed afterwards.  Every pointer a launch carries is a workspace
@@ -659,7 +705,7 @@ void Context::ctc_dev(const float* d_enc, int batch, int frames, int32_t* d_ids)
         in.pl = Planes{encpl_.as<__nv_bfloat16>(), encpl_.as<__nv_bfloat16>() + m_max_ * kDenc};
         launch_split_planes(d_enc, (int64_t)M * kDenc, in.pl, stream_);
     }
-    projector(ctc_, in, batch, frames, nullptr);
+    projector(ctc_, in, batch, frames, nullptr, false);
     float* x = x_.as<float>();
     tap("ctc_h", x, M, kDenc);
     if (f32) {
@@ -790,7 +836,7 @@ void Context::front_half_host(const float* audio, int batch, int64_t s_phys, con
     };
     for (int b0 = 0; b0 < batch; b0 += max_batch_) {
         const int nb = std::min(max_batch_, batch - b0);
-        stage_lengths(nb, s_phys, ilens + b0);
+        stage_lengths(nb, s_phys, ilens + b0, !use_graph(nb));
         if (use_graph(nb)) {
             // launch-bound regime: one upload, one graph (front end, encoder, adaptor and, if asked for, the CTC head),
             // downloads behind it on the same stream

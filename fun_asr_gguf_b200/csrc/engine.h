@@ -110,13 +110,13 @@ private:
     void build_planes(Linear& l);
     void linear(const Act& a, const Linear& w, int m, const Epilogue& ep);
     void attention(const float* qkv, int ld, int d_model, int batch, int frames, int heads, const int* kv_len,
-                   float* ctx_f32, Planes ctx_pl, int ldo);
+                   float* ctx_f32, Planes ctx_pl, int ldo, const Packing* pk = nullptr);
     void sanm_layer(const SanmLayer& L, bool first, int batch, int frames);
-    void projector(const Projector& P, const Act& in, int batch, int frames, const int* kv_len);
+    void projector(const Projector& P, const Act& in, int batch, int frames, const int* kv_len, bool packed);
     void tap(const char* name, const float* d, int64_t rows, int64_t cols);
     void ensure_room(int batch, int64_t s_phys) const;
     // encode_dev in three parts, so that the host variants can overlap copies with the front end
-    void stage_lengths(int batch, int64_t s_phys, const int64_t* h_ilens);
+    void stage_lengths(int batch, int64_t s_phys, const int64_t* h_ilens, bool allow_packed);
     void front_end(const float* d_audio, int b0, int nb, int64_t s_phys);
     void encoder_graph(int batch, int64_t s_phys, float* d_enc, float* d_adaptor, bool record_events = true);
     // Small batches are launch-bound (some 620 launches per 60 s segment against a few milliseconds of GPU work):
@@ -142,6 +142,7 @@ private:
     cudaStream_t stream_ = nullptr;
     cudaStream_t copy_stream_ = nullptr;      // host<->device copies of the host variants, overlapped with compute
     cudaEvent_t ev_up_[8] = {}, ev_enc_ = nullptr, ev_ad_ = nullptr;
+    bool capturable_ = true;                  // stream_ can be captured into a CUDA graph (not the legacy default stream)
     bool own_stream_ = true, finalized_ = false, taps_on_ = false, simt_attention_ = true;
 
     struct HostTensor { std::vector<int64_t> shape; std::unique_ptr<DevBuf> buf; };
@@ -164,7 +165,14 @@ private:
     int* d_nvalid_ = nullptr;
     int* d_tvalid_ = nullptr;
     int* d_tlen_ = nullptr;
-    int* h_lens_ = nullptr;      // pinned staging for the three length vectors
+    int* h_lens_ = nullptr;      // pinned staging for the length vectors and the packing tables
+    // Padding-free execution of the encoder and the adaptor (kernels.h Packing): chosen per call by stage_lengths when
+    // the batch holds padded frames and is not replayed as a CUDA graph (a graph's launch geometry is fixed)
+    bool packed_ = false, allow_packed_env_ = true;
+    Packing pk_;
+    int len_ints_ = 0;           // ints per staging slot: 3 length vectors + seg_off, order, tile_off
+    const Packing* packing() const { return packed_ ? &pk_ : nullptr; }
+    int enc_rows(int batch, int frames) const { return packed_ ? pk_.total_rows : batch * frames; }
     static constexpr int kLenSlots = 4;       // ring of staging slots: a slot is reused once its upload has completed
     cudaEvent_t len_ev_[kLenSlots] = {};
     int len_next_ = 0;

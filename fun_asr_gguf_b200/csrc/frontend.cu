@@ -151,20 +151,22 @@ k_fbank(const float* __restrict__ audio, int64_t s_phys, const int* __restrict__
 
 __global__ void __launch_bounds__(160)
 k_lfr_embed(const float* __restrict__ logmel, int t_mel, int t_lfr, const int* __restrict__ n_valid,
-            const float* __restrict__ pos_enc, float* __restrict__ x0, float* __restrict__ lfr_raw) {
+            const float* __restrict__ pos_enc, float* __restrict__ x0, float* __restrict__ lfr_raw,
+            const int* __restrict__ seg_off) {
     grid_dependency_wait();
     const int t = blockIdx.x, b = blockIdx.y, c4 = threadIdx.x;
     if (c4 >= kDin / 4) return;
     const int nv = n_valid[b];
     const int t_mel_valid = nv / kHop + 1;
     const int t_valid = (t_mel_valid + kLfrN - 1) / kLfrN;
+    if (seg_off && t >= t_valid) return;                       // packed layout: padded frames have no row
     const int col = c4 * 4, slot = col / kMels, j = col - slot * kMels;
     int src = t * kLfrN + slot - (kLfrM - 1) / 2;
     src = max(0, min(src, t_mel - 1));
     src = min(src, t_mel_valid - 1);
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (t < t_valid) v = *reinterpret_cast<const float4*>(&logmel[((int64_t)b * t_mel + src) * kMels + j]);
-    const int64_t o = ((int64_t)b * t_lfr + t) * kDin + col;
+    const int64_t o = (seg_off ? (int64_t)seg_off[b] + t : (int64_t)b * t_lfr + t) * kDin + col;
     if (lfr_raw) *reinterpret_cast<float4*>(&lfr_raw[o]) = v;
     const float s = 22.627416610717773f;      // fp32(512 ** 0.5), model_definition.py:206
     const float4 pe = *reinterpret_cast<const float4*>(&pos_enc[(int64_t)t * kDin + col]);
@@ -194,8 +196,8 @@ void launch_fbank(const float* audio, int batch, int64_t s_phys, const int* n_va
 }
 
 void launch_lfr_embed(const float* logmel, int batch, int t_mel, int t_lfr, const int* n_valid, const float* pos_enc,
-                      float* x0, float* lfr_raw, cudaStream_t st) {
-    FA_LAUNCH(k_lfr_embed, dim3(t_lfr, batch), 160, 0, st, logmel, t_mel, t_lfr, n_valid, pos_enc, x0, lfr_raw);
+                      float* x0, float* lfr_raw, cudaStream_t st, const int* seg_off) {
+    FA_LAUNCH(k_lfr_embed, dim3(t_lfr, batch), 160, 0, st, logmel, t_mel, t_lfr, n_valid, pos_enc, x0, lfr_raw, seg_off);
 }
 
 }  // namespace fa

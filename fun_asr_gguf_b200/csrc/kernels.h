@@ -12,6 +12,18 @@ void attention_init_device();
 void attention_tc_init_device();
 void tc_init_device();
 
+// Padding-free ("packed") row layout of a mixed-length batch (BASELINE configs[2], model_definition_paddable path):
+// segment b's valid frames are rows seg_off[b] .. seg_off[b] + t_valid[b] - 1 of every activation matrix of the encoder
+// and the adaptor, so the projections, LayerNorm, the memory block and the attention queries only ever see rows the
+// reference does not define as zero.  All arrays live in device memory and are staged per call.
+struct Packing {
+    const int* seg_off = nullptr;    // [batch + 1] first packed row of each segment
+    const int* order = nullptr;      // [batch] segments by decreasing length: the order attention items are dealt in
+    const int* tile_off = nullptr;   // [batch + 1] prefix sums of 128-query tiles, in `order`
+    int total_rows = 0, total_tiles = 0, max_len = 0;
+    double sum_len_sq = 0.0;         // sum of t_valid^2: attention FLOP accounting
+};
+
 // ---------------------------------------------------------------- front end (§8a a1-a4)
 // Per-segment sum of the valid samples, as kMeanParts double partials per segment.
 constexpr int kMeanParts = 64;
@@ -35,8 +47,10 @@ void launch_fbank_tc(const float* audio, int batch, int64_t s_phys, const int* n
                      float* logmel, int t_mel, cudaStream_t st);
 constexpr int kDftLd = 416;   // 402 real columns (201 cos + 201 -sin), padded
 // LFR stacking with replicate padding, frame mask, sqrt(512) scale and positional table.
+// seg_off != nullptr: only the valid frames are written, frame t of segment b to packed row seg_off[b] + t.
 void launch_lfr_embed(const float* logmel, int batch, int t_mel, int t_lfr, const int* n_valid, const float* pos_enc,
-                      float* x0 /*[B*T][560]*/, float* lfr_raw /*optional tap [B*T][560]*/, cudaStream_t st);
+                      float* x0 /*[B*T][560]*/, float* lfr_raw /*optional tap [B*T][560]*/, cudaStream_t st,
+                      const int* seg_off = nullptr);
 
 // ---------------------------------------------------------------- row kernels (§8a a5, a7, a12)
 struct Planes {           // bf16 hi/lo planes of an [M][ld] activation; lo may be null (bf16 mode)
@@ -44,13 +58,19 @@ struct Planes {           // bf16 hi/lo planes of an [M][ld] activation; lo may 
     __nv_bfloat16* lo = nullptr;
 };
 // y = LN(x) * gamma + beta (optionally zeroing rows t >= t_valid[b]); writes fp32 and/or planes.
+// seg_off != nullptr ("unpack"): x is packed, the outputs are physical [batch * frames] rows: row (b, t) is
+// LN(x[seg_off[b] + t]) for t < t_valid[b] and zero otherwise (rows = batch * frames, t_valid required).
 void launch_layernorm(const float* x, int rows, int d, const float* gamma, const float* beta, float eps,
-                      const int* t_valid /*nullable*/, int frames, float* y_f32, Planes y_pl, cudaStream_t st);
+                      const int* t_valid /*nullable*/, int frames, float* y_f32, Planes y_pl, cudaStream_t st,
+                      const int* seg_off = nullptr);
 // FSMN memory block: out = (resid ? resid : 0) + depthwise_conv11(v*m) + v*m.   v has row stride ldv.
+// pk != nullptr: packed rows; segment b is rows seg_off[b] .. + t_valid[b] - 1 (`frames` is then ignored).
 void launch_fsmn(const float* v, int ldv, const float* w /*[512][11]*/, const int* t_valid, int batch, int frames,
-                 const float* resid, float* out, cudaStream_t st);
+                 const float* resid, float* out, cudaStream_t st, const Packing* pk = nullptr);
 // out[b,t,:] = t < keep[b] ? in[b,t,:] : 0
-void launch_row_keep(const float* in, float* out, int batch, int frames, int d, const int* keep, cudaStream_t st);
+// seg_off != nullptr: `in` is packed (row (b, t) read from seg_off[b] + t), `out` physical
+void launch_row_keep(const float* in, float* out, int batch, int frames, int d, const int* keep, cudaStream_t st,
+                     const int* seg_off = nullptr);
 // fp32 -> planes
 void launch_split_planes(const float* x, int64_t n, Planes out, cudaStream_t st);
 // ids[r] = first argmax over logits[r][0..n)
@@ -144,7 +164,9 @@ void launch_attention_simt(const float* q, const float* k, const float* v, int l
 
 // tcgen05 attention on bf16 planes of a fused [rows][ld] q|k|v matrix (q pre-scaled by d_k^-0.5 * log2 e):
 // q at column 0, k at d_model, v at 2*d_model; head h at +h*dk.  Two planes `plane_stride` elements apart.
+// pk != nullptr: packed rows (kernels.h Packing); kv_len[b] is then both the key and the query count of segment b.
 void launch_attention_tc(Planes qkv, int64_t plane_stride, int ld, int d_model, int batch, int frames, int heads, int dk,
-                         const int* kv_len, float* ctx_f32, Planes ctx_pl, int ldo, cudaStream_t st);
+                         const int* kv_len, float* ctx_f32, Planes ctx_pl, int ldo, cudaStream_t st,
+                         const Packing* pk = nullptr);
 
 }  // namespace fa

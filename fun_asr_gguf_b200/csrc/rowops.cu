@@ -23,7 +23,8 @@ __global__ void __launch_bounds__(256)
 k_layernorm(const float* x, int rows, int d, const float* __restrict__ gamma,
             const float* __restrict__ beta, float eps, const int* __restrict__ t_valid, int frames,
             float* y /* may alias x: a warp reads its rows before it writes them */,
-            __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo) {
+            __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo,
+            const int* __restrict__ seg_off /* unpack: x packed, outputs physical */) {
     grid_dependency_wait();
     const int row0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * kLnRows, lane = threadIdx.x & 31;
     if (row0 >= rows) return;
@@ -31,8 +32,14 @@ k_layernorm(const float* x, int rows, int d, const float* __restrict__ gamma,
     float4 v[kLnRows][NV];
 #pragma unroll
     for (int r = 0; r < kLnRows; ++r) {
-        const bool have = row0 + r < rows;
-        const float4* xr = reinterpret_cast<const float4*>(x + (int64_t)(row0 + r) * d);
+        bool have = row0 + r < rows;
+        int64_t src = row0 + r;
+        if (seg_off && have) {
+            const int b = (row0 + r) / frames, t = (row0 + r) - b * frames;
+            have = t < t_valid[b];
+            src = (int64_t)seg_off[b] + t;
+        }
+        const float4* xr = reinterpret_cast<const float4*>(x + src * d);
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             const int idx = lane + 32 * i;
@@ -101,11 +108,14 @@ constexpr int kFsmnT = 8;
 
 __global__ void __launch_bounds__(kDenc / 4)
 k_fsmn(const float* __restrict__ v, int ldv, const float* __restrict__ w, const int* __restrict__ t_valid,
-       int frames, const float* resid, float* out) {
+       int frames, const float* resid, float* out, const int* __restrict__ seg_off) {
     grid_dependency_wait();
     const int c = threadIdx.x * 4, b = blockIdx.y, t0 = blockIdx.x * kFsmnT;
     const int tv = t_valid[b];
-    const float* vb = v + (int64_t)b * frames * ldv + c;
+    // packed layout: the segment is rows seg_off[b] .. + tv - 1 and has no padded frames
+    const int64_t base = seg_off ? seg_off[b] : (int64_t)b * frames;
+    if (seg_off) { frames = tv; if (t0 >= tv) return; }
+    const float* vb = v + base * ldv + c;
     float4 win[kFsmnT + kFsmnK - 1];
 #pragma unroll
     for (int i = 0; i < kFsmnT + kFsmnK - 1; ++i) {
@@ -117,7 +127,7 @@ k_fsmn(const float* __restrict__ v, int ldv, const float* __restrict__ w, const 
 #pragma unroll
         for (int i = 0; i < kFsmnT; ++i) {
             const int t = t0 + i;
-            rs[i] = t < frames ? *reinterpret_cast<const float4*>(resid + ((int64_t)b * frames + t) * kDenc + c)
+            rs[i] = t < frames ? *reinterpret_cast<const float4*>(resid + (base + t) * kDenc + c)
                                : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
@@ -144,7 +154,7 @@ k_fsmn(const float* __restrict__ v, int ldv, const float* __restrict__ w, const 
             r.x = __fadd_rn(rs[i].x, r.x); r.y = __fadd_rn(rs[i].y, r.y);
             r.z = __fadd_rn(rs[i].z, r.z); r.w = __fadd_rn(rs[i].w, r.w);
         }
-        *reinterpret_cast<float4*>(out + ((int64_t)b * frames + t) * kDenc + c) = r;
+        *reinterpret_cast<float4*>(out + (base + t) * kDenc + c) = r;
     }
 }
 
@@ -246,13 +256,14 @@ k_fsmn_stream(const float* __restrict__ v, int ldv, const float* __restrict__ w,
 
 __global__ void __launch_bounds__(256)
 k_row_keep(const float4* __restrict__ in, float4* __restrict__ out, int frames, int d4, const int* __restrict__ keep,
-           int64_t total4) {
+           int64_t total4, const int* __restrict__ seg_off) {
     grid_dependency_wait();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total4) return;
     const int64_t row = i / d4;
     const int b = (int)(row / frames), t = (int)(row - (int64_t)b * frames);
-    out[i] = t < keep[b] ? in[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const int64_t src = seg_off ? ((int64_t)seg_off[b] + t) * d4 + (i - row * d4) : i;
+    out[i] = t < keep[b] ? in[src] : make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 __global__ void __launch_bounds__(256)
@@ -501,31 +512,34 @@ k_ctc_collapse(const int32_t* __restrict__ ids, int frames, int blank, int32_t* 
 }  // namespace
 
 void launch_layernorm(const float* x, int rows, int d, const float* gamma, const float* beta, float eps,
-                      const int* t_valid, int frames, float* y_f32, Planes y_pl, cudaStream_t st) {
+                      const int* t_valid, int frames, float* y_f32, Planes y_pl, cudaStream_t st, const int* seg_off) {
     FA_REQUIRE(d % 4 == 0 && d <= 128 * kLnMaxVec, "layernorm width must be a multiple of 4 and <= 1024");
+    FA_REQUIRE(!seg_off || (t_valid && y_f32 != x), "layernorm unpack needs the length vector and an output that is not its input");
     // algorithmic bytes: the row in, and whichever outputs are written (fp32 row, bf16 hi plane, bf16 lo plane)
     prof_note_work(0.0, (double)rows * d * (4.0 + (y_f32 ? 4.0 : 0.0) + (y_pl.hi ? 2.0 : 0.0) + (y_pl.lo ? 2.0 : 0.0)));
     // d <= 512 (141 of the 155 launches of a step): one row per warp — 40 registers, 48 resident warps per SM; two rows
     // per warp (62 registers) measured 6 % slower on the same box, four rows 18 % slower
     if (d <= 512) {
-        FA_LAUNCH((k_layernorm<4, 1>), cdiv(rows, 8), 256, 0, st, x, rows, d, gamma, beta, eps, t_valid, frames, y_f32, y_pl.hi, y_pl.lo);
+        FA_LAUNCH((k_layernorm<4, 1>), cdiv(rows, 8), 256, 0, st, x, rows, d, gamma, beta, eps, t_valid, frames, y_f32, y_pl.hi, y_pl.lo, seg_off);
         return;
     }
     const int grid = cdiv(rows, 8 * 2);
     if (d <= 640) {
-        FA_LAUNCH(k_layernorm<5>, grid, 256, 0, st, x, rows, d, gamma, beta, eps, t_valid, frames, y_f32, y_pl.hi, y_pl.lo);
+        FA_LAUNCH(k_layernorm<5>, grid, 256, 0, st, x, rows, d, gamma, beta, eps, t_valid, frames, y_f32, y_pl.hi, y_pl.lo, seg_off);
     } else {
-        FA_LAUNCH(k_layernorm<8>, grid, 256, 0, st, x, rows, d, gamma, beta, eps, t_valid, frames, y_f32, y_pl.hi, y_pl.lo);
+        FA_LAUNCH(k_layernorm<8>, grid, 256, 0, st, x, rows, d, gamma, beta, eps, t_valid, frames, y_f32, y_pl.hi, y_pl.lo, seg_off);
     }
 }
 
 void launch_fsmn(const float* v, int ldv, const float* w, const int* t_valid, int batch, int frames,
-                 const float* resid, float* out, cudaStream_t st) {
+                 const float* resid, float* out, cudaStream_t st, const Packing* pk) {
+    const int* seg_off = pk ? pk->seg_off : nullptr;
+    if (pk) frames = pk->max_len;
     FA_REQUIRE(ldv % 4 == 0, "fsmn input stride must be a multiple of 4");
     FA_REQUIRE(resid == nullptr || resid != v, "fsmn: the residual may alias the output, not the input");
-    prof_note_work(0.0, (double)batch * frames * kDenc * 4.0 * (resid ? 3.0 : 2.0));    // v in, residual in, x out
+    prof_note_work(0.0, (pk ? (double)pk->total_rows : (double)batch * frames) * kDenc * 4.0 * (resid ? 3.0 : 2.0));    // v in, residual in, x out
     const char* fe = getenv("FUNASR_B200_FSMN");                          // comparison aid, read at every launch
-    const bool strips = !(fe && !strcmp(fe, "stream"));                     // the streaming kernel measured equal (4.07 vs 4.08 ms per step): strips stay the default
+    const bool strips = seg_off || !(fe && !strcmp(fe, "stream"));                     // the streaming kernel measured equal (4.07 vs 4.08 ms per step): strips stay the default
     static int sms = 0;
     if (!strips && sms == 0) {
         int dev = 0;
@@ -534,17 +548,18 @@ void launch_fsmn(const float* v, int ldv, const float* w, const int* t_valid, in
         FA_CUDA(cudaFuncSetAttribute(k_fsmn_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, kFsSmem));
     }
     if (strips) {
-        FA_LAUNCH(k_fsmn, dim3(cdiv(frames, kFsmnT), batch), kDenc / 4, 0, st, v, ldv, w, t_valid, frames, resid, out);
+        FA_LAUNCH(k_fsmn, dim3(cdiv(frames, kFsmnT), batch), kDenc / 4, 0, st, v, ldv, w, t_valid, frames, resid, out, seg_off);
         return;
     }
     const int total = batch * cdiv(frames, kFsT);
     FA_LAUNCH(k_fsmn_stream, total < sms ? total : sms, kFsThreads, kFsSmem, st, v, ldv, w, t_valid, batch, frames, resid, out);
 }
 
-void launch_row_keep(const float* in, float* out, int batch, int frames, int d, const int* keep, cudaStream_t st) {
+void launch_row_keep(const float* in, float* out, int batch, int frames, int d, const int* keep, cudaStream_t st,
+                     const int* seg_off) {
     const int64_t total4 = (int64_t)batch * frames * d / 4;
     FA_LAUNCH(k_row_keep, cdiv(total4, 256), 256, 0, st, reinterpret_cast<const float4*>(in),
-              reinterpret_cast<float4*>(out), frames, d / 4, keep, total4);
+              reinterpret_cast<float4*>(out), frames, d / 4, keep, total4, seg_off);
 }
 
 void launch_split_planes(const float* x, int64_t n, Planes out, cudaStream_t st) {
