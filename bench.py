@@ -412,7 +412,7 @@ def run_ours(args) -> None:
             break
         except (OSError, ValueError, KeyError):
             continue
-    mma_factor = {"bf16x3": 3, "bf16": 1, "fp32": 1}[args.precision]
+    mma_factor = {"bf16x3": 3, "bf16": 1, "fp8": 1, "fp32": 1}[args.precision]
     peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback 1.4 PF sustained"
     if args.precision == "fp32":
@@ -499,7 +499,10 @@ def run_ours(args) -> None:
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": P0.scaling, "vs_baseline": None,
         "dtype": {"bf16x3": "bf16x3 (projections and attention: bf16 hi+lo planes on tcgen05, 3 MMAs per product, fp32 accumulate; fp32 softmax, LayerNorm, FSMN, front end)",
-                  "bf16": "bf16 (projections plain bf16 on tcgen05, attention bf16x3, fp32 accumulate; speed mode, not token-exact)", "fp32": "f32"}[args.precision],
+                  "bf16": "bf16 (projections plain bf16 on tcgen05, attention bf16x3, fp32 accumulate; speed mode, not token-exact)",
+                  "fp8": "fp8 (projections e4m3 x e4m3 on tcgen05 kind::f8f6f4 with per-output-channel weight scales; attention bf16x3, its output "
+                         "projection bf16, fp32 accumulate, fp32 LayerNorm/softmax; SPEED MODE with an id-mismatch budget, not token-exact)",
+                  "fp32": "f32"}[args.precision],
         "data": "synthetic (0.1*N(0,1) clipped, seed 1234+i); random-init weights of the architecture (no checkpoint ships)",
         "config": {"workload": WORKLOADS[args.workload], "segments_per_step_this_rank": sum(h.shape[0] for h, _ in P0.batches),
                    "batches_per_step_this_rank": len(P0.batches), "segment_s": SEG_S, "audio_s_per_step_all_ranks": audio_s_total / args.steps,
@@ -528,7 +531,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16", "fp8", "fp32"])
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--cpu-rows", type=int, default=12, help="rows of the batch the cpu_baseline / parity leg runs through the oracle")

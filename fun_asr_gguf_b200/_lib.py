@@ -8,7 +8,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libfunasr_b200.so")
 
-PREC = {"fp32": 0, "bf16x3": 1, "bf16": 2}
+PREC = {"fp32": 0, "bf16x3": 1, "bf16": 2, "fp8": 3}
 
 c_float_p = C.POINTER(C.c_float)
 c_i64_p = C.POINTER(C.c_int64)

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp8.h>
 #include <cstdint>
 #include <cstdio>
 #include <stdexcept>
@@ -88,5 +89,14 @@ __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uin
     const __nv_bfloat162 l = __floats2bfloat162_rn(a - ha, b - hb);
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
+
+#ifdef __CUDACC__
+// Four floats -> four e4m3 bytes (element 0 in the low byte): round to nearest even, saturating at +-448.
+__device__ __forceinline__ uint32_t f32x4_to_e4m3(float a, float b, float c, float d) {
+    const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E4M3);
+    const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(c, d), __NV_SATFINITE, __NV_E4M3);
+    return lo | (hi << 16);
+}
+#endif
 
 }  // namespace fa

@@ -93,7 +93,7 @@ int target_len_of(int64_t n_valid) {
 Context::Context(int device, int max_batch, int64_t max_samples, int precision)
     : device_(device), max_batch_(max_batch), prec_(precision), max_samples_(max_samples) {
     FA_REQUIRE(max_batch >= 1 && max_samples >= 1, "max_batch and max_samples must be positive");
-    FA_REQUIRE(precision >= kFp32 && precision <= kBf16, "unknown precision mode");
+    FA_REQUIRE(precision >= kFp32 && precision <= kFp8, "unknown precision mode");
     int count = 0;
     FA_CUDA(cudaGetDeviceCount(&count));
     FA_REQUIRE(device >= 0 && device < count, "no such CUDA device");
@@ -182,6 +182,16 @@ void Context::build_planes(Linear& l) {
     l.planes = b.as<__nv_bfloat16>();
     launch_split_planes(l.w, n, Planes{l.planes, l.planes + n}, stream_);
     l.op = tc_make_weight(l.planes, l.n, l.k, n, 2);
+    if (prec_ == kFp8 && l.k % 16 == 0) {
+        derived_.emplace_back(new DevBuf);
+        DevBuf& q = *derived_.back();
+        const size_t scale_off = ((size_t)n + 255) / 256 * 256;
+        q.alloc(scale_off + (size_t)l.n * sizeof(float));
+        l.w8 = q.as<uint8_t>();
+        l.wscale = reinterpret_cast<float*>(q.as<uint8_t>() + scale_off);
+        launch_quant_rows_e4m3(l.w, l.n, l.k, l.w8, l.wscale, stream_);
+        l.op8 = tc_make_operand_f8(l.w8, l.n, l.k, l.k, 64);
+    }
 }
 
 Linear Context::make_linear_from(const float* w, const float* b, int n, int k) {
@@ -266,7 +276,7 @@ void Context::finalize() {
         ctc_lo_ = make_linear("ctc_proj.ctc_lo", vocab_, kDenc);
         // FUNASR_B200_VOCAB=full keeps the three-product projection with the fused running argmax (comparison aid)
         const char* vm = getenv("FUNASR_B200_VOCAB");
-        vocab_rescore_ = prec_ == kBf16x3 && !(vm && std::string(vm) == "full");
+        vocab_rescore_ = prec_ != kFp32 && !(vm && std::string(vm) == "full");
         if (vocab_rescore_) {
             DevBuf nm;
             nm.alloc(sizeof(float));
@@ -352,6 +362,11 @@ void Context::finalize() {
         ctxpl_.alloc(2 * M * kDllm * 2);
         ffnpl_.alloc(2 * M * kDffn * 2);
         encpl_.alloc(2 * M * kDenc * 2);
+        if (prec_ == kFp8) {
+            h8_.alloc(M * kDllm);
+            ffn8_.alloc(M * kDffn);
+            enc8_.alloc(M * kDenc);
+        }
         const size_t tiles = (size_t)tc_argmax_tiles(vocab_);
         amax_val_.alloc(M * tiles * 4);
         amax_idx_.alloc(M * tiles * 4);
@@ -382,6 +397,7 @@ void Context::finalize() {
 Act Context::h_act(int ld) const {
     Act a; a.ld = ld; a.f32 = h32_.as<float>();
     if (hpl_.p) a.pl = Planes{hpl_.as<__nv_bfloat16>(), hpl_.as<__nv_bfloat16>() + m_max_ * kDllm};
+    a.f8 = h8_.as<uint8_t>();
     return a;
 }
 Act Context::ctx_act(int ld) const {
@@ -392,14 +408,22 @@ Act Context::ctx_act(int ld) const {
 Act Context::ffn_act(int ld) const {
     Act a; a.ld = ld; a.f32 = ffn32_.as<float>();
     if (ffnpl_.p) a.pl = Planes{ffnpl_.as<__nv_bfloat16>(), ffnpl_.as<__nv_bfloat16>() + m_max_ * kDffn};
+    a.f8 = ffn8_.as<uint8_t>();
     return a;
 }
 
-static Epilogue into(const Act& dst, bool fp32_mode) {
+static Epilogue into(const Act& dst, int prec) {
     Epilogue e;
-    if (fp32_mode) { e.out_f32 = const_cast<float*>(dst.f32); e.ldc = dst.ld; }
+    if (prec == kFp32) { e.out_f32 = const_cast<float*>(dst.f32); e.ldc = dst.ld; }
+    else if (prec == kFp8 && dst.f8) { e.out_f8 = dst.f8; e.ld8 = dst.ld; }
     else { e.out_pl = dst.pl; e.ldp = dst.ld; }
     return e;
+}
+
+void Context::layernorm_to(const float* x, int rows, int d, const float* g, const float* b, float eps, const Act& dst) {
+    if (prec_ == kFp32) launch_layernorm(x, rows, d, g, b, eps, nullptr, 0, const_cast<float*>(dst.f32), Planes{}, stream_);
+    else if (prec_ == kFp8 && dst.f8) launch_layernorm(x, rows, d, g, b, eps, nullptr, 0, nullptr, Planes{}, stream_, nullptr, dst.f8);
+    else launch_layernorm(x, rows, d, g, b, eps, nullptr, 0, nullptr, dst.pl, stream_);
 }
 
 void Context::linear(const Act& a, const Linear& w, int m, const Epilogue& ep_in) {
@@ -407,6 +431,11 @@ void Context::linear(const Act& a, const Linear& w, int m, const Epilogue& ep_in
     ep.bias = w.b;
     if (prec_ == kFp32) {
         launch_gemm_simt(a.f32, a.ld, w.w, m, w.n, w.k, ep, stream_);
+    } else if (prec_ == kFp8 && a.f8 && w.w8) {
+        // e4m3 x e4m3 (activations as they are, weights per output channel): acc * wscale[col] + bias
+        const TcOperand opa = tc_make_operand_f8(a.f8, m, w.k, a.ld, kTcBlockM);
+        ep.f8 = true; ep.col_scale = w.wscale;
+        launch_gemm_tc(opa, w.op8, m, w.n, w.k, 1, ep, stream_);
     } else {
         const int64_t plane_stride = a.pl.lo - a.pl.hi;
         const TcOperand opa = tc_make_operand(a.pl.hi, m, w.k, a.ld, plane_stride, 2, kTcBlockM);
@@ -484,8 +513,7 @@ void Context::sanm_layer(const SanmLayer& L, bool first, int batch, int frames) 
     float* x = x_.as<float>();
     const float* xin = first ? x0_.as<float>() : x;
     const Act h = h_act(L.d_in);
-    launch_layernorm(xin, M, L.d_in, L.ln1_g, L.ln1_b, 1e-5f, nullptr, frames, f32 ? const_cast<float*>(h.f32) : nullptr,
-                     f32 ? Planes{} : h.pl, stream_);
+    layernorm_to(xin, M, L.d_in, L.ln1_g, L.ln1_b, 1e-5f, h);
     linear(h, L.qkv, M, qkv_epilogue(kDenc, 4, true));      // fp32 v feeds the FSMN branch
     const float* qkv = qkv_.as<float>();
     // x <- (x) + fsmn(v*m): the memory branch plus, except in layer 0, the block's residual
@@ -498,10 +526,9 @@ void Context::sanm_layer(const SanmLayer& L, bool first, int batch, int frames) 
     linear(c, L.out, M, eo);
     if (first) return;
     const Act h2 = h_act(kDenc);
-    launch_layernorm(x, M, kDenc, L.ln2_g, L.ln2_b, 1e-5f, nullptr, frames, f32 ? const_cast<float*>(h2.f32) : nullptr,
-                     f32 ? Planes{} : h2.pl, stream_);
+    layernorm_to(x, M, kDenc, L.ln2_g, L.ln2_b, 1e-5f, h2);
     const Act f = ffn_act(kDffn);
-    Epilogue e1 = into(f, f32);
+    Epilogue e1 = into(f, prec_);
     e1.relu = true;
     linear(h2, L.w1, M, e1);
     Epilogue e2;
@@ -515,7 +542,7 @@ void Context::projector(const Projector& P, const Act& in, int batch, int frames
     const bool f32 = prec_ == kFp32;
     float* x = x_.as<float>();
     const Act f = ffn_act(kDffn);
-    Epilogue e1 = into(f, f32);
+    Epilogue e1 = into(f, prec_);
     e1.relu = true;
     linear(in, P.lin1, M, e1);
     Epilogue e2;
@@ -523,8 +550,7 @@ void Context::projector(const Projector& P, const Act& in, int batch, int frames
     linear(f, P.lin2, M, e2);
     for (const MhaBlock& B : P.blocks) {
         const Act h = h_act(d);
-        launch_layernorm(x, M, d, B.ln1_g, B.ln1_b, 1e-12f, nullptr, frames, f32 ? const_cast<float*>(h.f32) : nullptr,
-                         f32 ? Planes{} : h.pl, stream_);
+        layernorm_to(x, M, d, B.ln1_g, B.ln1_b, 1e-12f, h);
         linear(h, B.qkv, M, qkv_epilogue(d, P.heads, false));
         const Act c = ctx_act(d);
         attention(qkv_.as<float>(), 3 * d, d, batch, frames, P.heads, kv_len, f32 ? const_cast<float*>(c.f32) : nullptr,
@@ -532,10 +558,9 @@ void Context::projector(const Projector& P, const Act& in, int batch, int frames
         Epilogue eo;
         eo.resid = x; eo.ldr = d; eo.out_f32 = x; eo.ldc = d;
         linear(c, B.out, M, eo);
-        launch_layernorm(x, M, d, B.ln2_g, B.ln2_b, 1e-12f, nullptr, frames, f32 ? const_cast<float*>(h.f32) : nullptr,
-                         f32 ? Planes{} : h.pl, stream_);
+        layernorm_to(x, M, d, B.ln2_g, B.ln2_b, 1e-12f, h);
         const Act ff = ffn_act(d / 4);
-        Epilogue ea = into(ff, f32);
+        Epilogue ea = into(ff, prec_);
         ea.relu = true;
         linear(h, B.w1, M, ea);
         Epilogue eb;
@@ -638,15 +663,17 @@ void Context::encoder_graph(int batch, int64_t s_phys, float* d_enc, float* d_ad
     const bool f32 = prec_ == kFp32;
     Planes encpl;
     if (!f32) encpl = Planes{encpl_.as<__nv_bfloat16>(), encpl_.as<__nv_bfloat16>() + m_max_ * kDenc};
-    Act in; in.f32 = d_enc; in.pl = encpl; in.ld = kDenc;
+    const bool f8 = prec_ == kFp8;
+    Act in; in.f32 = d_enc; in.pl = encpl; in.f8 = enc8_.as<uint8_t>(); in.ld = kDenc;
     if (pk) {
         // enc_output leaves in the reference's physical [batch][frames] shape, padded frames zero (the CTC head runs on
         // it as it is: unmasked, every physical frame — F7); the adaptor goes on with the packed rows
-        launch_layernorm(x, batch * frames, kDenc, tp_g_, tp_b_, 1e-5f, d_tvalid_, frames, d_enc, encpl, stream_, seg_off);
-        in.pl = h_act(kDenc).pl;
-        launch_layernorm(x, M, kDenc, tp_g_, tp_b_, 1e-5f, nullptr, frames, nullptr, in.pl, stream_);
+        launch_layernorm(x, batch * frames, kDenc, tp_g_, tp_b_, 1e-5f, d_tvalid_, frames, d_enc, Planes{}, stream_, seg_off);
+        in = h_act(kDenc);
+        layernorm_to(x, M, kDenc, tp_g_, tp_b_, 1e-5f, in);
     } else {
-        launch_layernorm(x, M, kDenc, tp_g_, tp_b_, 1e-5f, d_tvalid_, frames, d_enc, encpl, stream_);
+        launch_layernorm(x, M, kDenc, tp_g_, tp_b_, 1e-5f, d_tvalid_, frames, d_enc, f8 ? Planes{} : encpl, stream_, nullptr,
+                         f8 ? in.f8 : nullptr);
     }
     if (record_events) FA_CUDA(cudaEventRecord(ev_enc_, stream_));       // enc_output is final: a download may start
 
@@ -701,7 +728,10 @@ void Context::ctc_dev(const float* d_enc, int batch, int frames, int32_t* d_ids)
     const int M = batch * frames;
     const bool f32 = prec_ == kFp32;
     Act in; in.f32 = d_enc; in.ld = kDenc;
-    if (!f32) {
+    if (prec_ == kFp8) {
+        in.f8 = enc8_.as<uint8_t>();
+        launch_to_e4m3(d_enc, (int64_t)M * kDenc, in.f8, stream_);
+    } else if (!f32) {
         in.pl = Planes{encpl_.as<__nv_bfloat16>(), encpl_.as<__nv_bfloat16>() + m_max_ * kDenc};
         launch_split_planes(d_enc, (int64_t)M * kDenc, in.pl, stream_);
     }
@@ -880,15 +910,34 @@ void Context::test_linear(const float* a, const float* w, const float* bias, con
     if (resid) { dr.alloc((size_t)m * n * 4); FA_CUDA(cudaMemcpy(dr.p, resid, dr.bytes, cudaMemcpyHostToDevice)); }
     Epilogue e;
     e.bias = db.as<float>(); e.resid = dr.as<float>(); e.ldr = n; e.relu = relu != 0; e.out_f32 = dout.as<float>(); e.ldc = n;
-    const int ldp = (n + 7) / 8 * 8;
-    if (out_planes_sum) {
+    const int ldp = precision == kFp8 ? (n + 15) / 16 * 16 : (n + 7) / 8 * 8;
+    if (out_planes_sum && precision != kFp8) {
         dpl_o.alloc((size_t)2 * m * ldp * 2);
         FA_CUDA(cudaMemsetAsync(dpl_o.p, 0, dpl_o.bytes, stream_));
         e.out_pl = Planes{dpl_o.as<__nv_bfloat16>(), dpl_o.as<__nv_bfloat16>() + (size_t)m * ldp};
         e.ldp = ldp;
     }
+    DevBuf d8a, d8w, d8o;
     if (precision == kFp32) {
         launch_gemm_simt(da.as<float>(), k, dw.as<float>(), m, n, k, e, stream_);
+    } else if (precision == kFp8) {
+        // e4m3 operands: activations converted as they are, weights per output channel; with out_planes_sum the e4m3
+        // output form is exercised too (handed back decoded)
+        FA_REQUIRE(k % 16 == 0, "fp8 test_linear needs K % 16 == 0");
+        const size_t scale_off = ((size_t)n * k + 255) / 256 * 256;
+        d8a.alloc((size_t)m * k); d8w.alloc(scale_off + (size_t)n * 4);
+        launch_to_e4m3(da.as<float>(), (int64_t)m * k, d8a.as<uint8_t>(), stream_);
+        float* sc = reinterpret_cast<float*>(d8w.as<uint8_t>() + scale_off);
+        launch_quant_rows_e4m3(dw.as<float>(), n, k, d8w.as<uint8_t>(), sc, stream_);
+        e.out_pl = Planes{}; e.ldp = 0;
+        if (out_planes_sum) {
+            d8o.alloc((size_t)m * ldp);
+            FA_CUDA(cudaMemsetAsync(d8o.p, 0, d8o.bytes, stream_));
+            e.out_f8 = d8o.as<uint8_t>(); e.ld8 = ldp;
+        }
+        e.f8 = true; e.col_scale = sc;
+        launch_gemm_tc(tc_make_operand_f8(d8a.as<uint8_t>(), m, k, k, kTcBlockM), tc_make_operand_f8(d8w.as<uint8_t>(), n, k, k, 64), m, n, k,
+                       1, e, stream_);
     } else {
         dpl_a.alloc((size_t)2 * m * k * 2); dpl_w.alloc((size_t)2 * n * k * 2);
         Planes pa{dpl_a.as<__nv_bfloat16>(), dpl_a.as<__nv_bfloat16>() + (size_t)m * k};
@@ -901,6 +950,18 @@ void Context::test_linear(const float* a, const float* w, const float* bias, con
     }
     FA_CUDA(cudaStreamSynchronize(stream_));
     FA_CUDA(cudaMemcpy(out, dout.p, dout.bytes, cudaMemcpyDeviceToHost));
+    if (out_planes_sum && precision == kFp8) {
+        std::vector<uint8_t> h8((size_t)m * ldp);
+        FA_CUDA(cudaMemcpy(h8.data(), d8o.p, d8o.bytes, cudaMemcpyDeviceToHost));
+        auto decode = [](uint8_t b) {                    // e4m3fn: 1-4-3, bias 7, no infinities
+            const int e = (b >> 3) & 15, mant = b & 7;
+            const float v = e == 0 ? std::ldexp((float)mant, -9) : std::ldexp(1.0f + mant / 8.0f, e - 7);
+            return (b & 0x80) ? -v : v;
+        };
+        for (int i = 0; i < m; ++i)
+            for (int j = 0; j < n; ++j) out_planes_sum[(size_t)i * n + j] = decode(h8[(size_t)i * ldp + j]);
+        return;
+    }
     if (out_planes_sum) {
         std::vector<__nv_bfloat16> hp((size_t)2 * m * ldp);
         FA_CUDA(cudaMemcpy(hp.data(), dpl_o.p, dpl_o.bytes, cudaMemcpyDeviceToHost));

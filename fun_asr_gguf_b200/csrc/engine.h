@@ -11,7 +11,7 @@
 
 namespace fa {
 
-enum Precision { kFp32 = 0, kBf16x3 = 1, kBf16 = 2 };
+enum Precision { kFp32 = 0, kBf16x3 = 1, kBf16 = 2, kFp8 = 3 };
 
 struct DevBuf {
     void* p = nullptr;
@@ -34,11 +34,15 @@ struct Linear {                 // one nn.Linear: y = x W^T + b
     int n = 0, k = 0;
     __nv_bfloat16* planes = nullptr;   // [2][n][k] bf16 hi|lo (tensor-core modes)
     TcOperand op;
+    uint8_t* w8 = nullptr;             // [n][k] e4m3(w / wscale[row]) (fp8 mode)
+    float* wscale = nullptr;           // [n] per-output-channel scale
+    TcOperand op8;
 };
 
 struct Act {                    // an activation matrix as the GEMMs consume it
     const float* f32 = nullptr; // fp32 mode
     Planes pl;                  // tensor-core modes
+    uint8_t* f8 = nullptr;      // fp8 mode: e4m3 bytes (null: this operand stays bf16 even in fp8 mode)
     int ld = 0;
 };
 
@@ -113,6 +117,8 @@ private:
                    float* ctx_f32, Planes ctx_pl, int ldo, const Packing* pk = nullptr);
     void sanm_layer(const SanmLayer& L, bool first, int batch, int frames);
     void projector(const Projector& P, const Act& in, int batch, int frames, const int* kv_len, bool packed);
+    // LayerNorm into the form the next projection reads at this precision (fp32 / bf16 planes / e4m3)
+    void layernorm_to(const float* x, int rows, int d, const float* g, const float* b, float eps, const Act& dst);
     void tap(const char* name, const float* d, int64_t rows, int64_t cols);
     void ensure_room(int batch, int64_t s_phys) const;
     // encode_dev in three parts, so that the host variants can overlap copies with the front end
@@ -159,7 +165,7 @@ private:
 
     // workspace
     DevBuf audio_, partials_, logmel_, x0_, x_, h32_, hpl_, qkv_, qkvpl_, ctx32_, ctxpl_, ffn32_, ffnpl_, encpl_, enc_,
-        adaptor_out_, ids_, amax_val_, amax_idx_, logits_, lens_, tokens_, cand_meta_, cand_list_, yplanes_, power_;
+        adaptor_out_, ids_, amax_val_, amax_idx_, logits_, lens_, tokens_, cand_meta_, cand_list_, yplanes_, power_, h8_, ffn8_, enc8_;
     float vocab_wnorm_ = 0.f;                 // max_c |w_c|_2 of ctc_lo (bound of the one-product vocabulary pass)
     bool vocab_rescore_ = false;              // bf16x3: one-product pass + exact rescoring of the candidates
     int* d_nvalid_ = nullptr;

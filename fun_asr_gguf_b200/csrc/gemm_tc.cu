@@ -81,6 +81,9 @@ struct EpiParams {
     const float* cand_bound2;
     int cand_cap;
     const int32_t* gate;                         // launch does nothing when *gate == 0
+    const float* col_scale;                      // fp8 mode: per-output-channel weight scale, applied to the accumulator before the bias
+    uint8_t* out_f8;                             // fp8 mode: e4m3 output [M][ld8] (the next projection's A operand)
+    int ld8;
     int ldr, ldc, ldp, relu, n_slots;            // n_slots: 128-column groups of N (fused argmax partials)
     float pl_col_scale;
     int pl_col_scale_end, f32_col_begin;
@@ -177,6 +180,17 @@ __device__ __forceinline__ void epilogue_unit(const EpiParams& ep, const CUtenso
         uint32_t r[32];
         tc_ld32(taddr + c * 32, r);
         tc_wait_ld();
+        if (ep.col_scale) {                                     // warp-uniform
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 s4 = col0 + 32 <= n ? __ldg(reinterpret_cast<const float4*>(ep.col_scale + col0) + j)
+                                                 : make_float4(1.f, 1.f, 1.f, 1.f);
+                r[4 * j] = __float_as_uint(__fmul_rn(__uint_as_float(r[4 * j]), s4.x));
+                r[4 * j + 1] = __float_as_uint(__fmul_rn(__uint_as_float(r[4 * j + 1]), s4.y));
+                r[4 * j + 2] = __float_as_uint(__fmul_rn(__uint_as_float(r[4 * j + 2]), s4.z));
+                r[4 * j + 3] = __float_as_uint(__fmul_rn(__uint_as_float(r[4 * j + 3]), s4.w));
+            }
+        }
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __fadd_rn(__uint_as_float(r[j]), bias[j]);
@@ -248,6 +262,17 @@ __device__ __forceinline__ void epilogue_unit(const EpiParams& ep, const CUtenso
                 bulk_commit();
             }
             store_pending = true;
+        }
+        if (ep.out_f8) {
+            // e4m3 (round to nearest even, saturating at +-448): a thread owns 32 consecutive bytes of its row, one sector
+            if (row < m && col0 + 32 <= n) {
+                uint32_t w8[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) w8[j] = f32x4_to_e4m3(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                uint4* dst = reinterpret_cast<uint4*>(ep.out_f8 + (int64_t)row * ep.ld8 + col0);
+                dst[0] = make_uint4(w8[0], w8[1], w8[2], w8[3]);
+                dst[1] = make_uint4(w8[4], w8[5], w8[6], w8[7]);
+            }
         }
         if (ep.out_hi) {
             if (col0 < ep.pl_col_scale_end) {                    // warp-uniform: the q columns of a fused q|k|v projection
@@ -461,6 +486,14 @@ __device__ __forceinline__ void tc_mma_pair(uint32_t tmem_d, uint64_t adesc, uin
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
         : "memory");
 }
+// the same on e4m3 operands (kind::f8f6f4: K = 32 per instruction, i.e. the same 32 bytes of a 128-byte swizzled row)
+__device__ __forceinline__ void tc_mma_pair_f8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n}\n"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
 // commit of the pair's MMAs: arrives on the barrier at this offset in BOTH CTAs
 __device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -486,7 +519,10 @@ __device__ __forceinline__ void unit_coords(int u, const Sched& s, int& mt, int&
     n0 = nt * BN + part * nw;
 }
 
-template <int NP>
+// F8: one plane of e4m3 bytes per operand (the reference's int8 graph variant, 02-Quantize-ONNX.py:41-44, as W8A8
+// floating point): a K-block is 128 elements = the same 128-byte rows, tcgen05.mma.kind::f8f6f4 takes K = 32 per
+// instruction, the per-output-channel weight scale is applied in the epilogue.  Everything else is the NP = 1 kernel.
+template <int NP, bool F8 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 k_gemm_tc2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
            const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_pl, int m, int n, int k,
@@ -505,7 +541,9 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
     const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     const int rank = (int)cluster_ctarank();                 // 0 = leader (issues the MMAs), 1 = peer
     const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
-    const int k_blocks = (k + BK - 1) / BK;
+    constexpr int kBKe = F8 ? 2 * BK : BK;                    // elements per K-block: 128 bytes of a row either way
+    static_assert(!F8 || NP == 1, "the fp8 kernel has one plane per operand");
+    const int k_blocks = (k + kBKe - 1) / kBKe;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::kStages; ++s) {
@@ -552,10 +590,10 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                         if (rank == 0) mbar_arrive_expect_tx(bar_full + 8 * stage, 2 * cta_bytes);
 #pragma unroll
                         for (int p = 0; p < NP; ++p) {
-                            tma_load_3d_pair(sbase + p * kATileBytes, &map_a, full, kb * BK, a_row, p);
+                            tma_load_3d_pair(sbase + p * kATileBytes, &map_a, full, kb * kBKe, a_row, p);
                             const uint32_t wdst = sbase + NP * kATileBytes + p * C::kHalfWBytes;
                             for (int r = 0; r < w_rows; r += 64)
-                                tma_load_3d_pair(wdst + r * BK * 2, &map_w, full, kb * BK, w_row + r, p);
+                                tma_load_3d_pair(wdst + r * BK * 2, &map_w, full, kb * kBKe, w_row + r, p);
                         }
                     }
                     __syncwarp();
@@ -574,7 +612,8 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                 int mt, n0, nw;
                 unit_coords(u, sched, mt, n0, nw);
                 // D = f32, A = B = bf16, K-major both, N = nw, M = 256 (128 rows in each CTA)
-                const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(nw >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+                // (F8: A = B = e4m3, format code 0)
+                const uint32_t idesc = (1u << 4) | (F8 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(nw >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
                 mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);       // both CTAs' epilogues have drained this accumulator
@@ -600,7 +639,8 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                         }
 #pragma unroll
                         for (int ks = 0; ks < BK / 16; ++ks) {
-                            tc_mma_pair(tmem_d, umma_desc_sw128(a_hi + ks * 32), umma_desc_sw128(w_hi + ks * 32), idesc, accum);
+                            if constexpr (F8) tc_mma_pair_f8(tmem_d, umma_desc_sw128(a_hi + ks * 32), umma_desc_sw128(w_hi + ks * 32), idesc, accum);
+                            else tc_mma_pair(tmem_d, umma_desc_sw128(a_hi + ks * 32), umma_desc_sw128(w_hi + ks * 32), idesc, accum);
                             accum = 1u;
                         }
                         tc_commit_pair(bar_empty + 8 * stage);            // frees this stage in both CTAs
@@ -917,6 +957,7 @@ void tc_init_device() {
     FA_CUDA(cudaFuncSetAttribute((k_gemm_tc<2, 64>), cudaFuncAttributeMaxDynamicSharedMemorySize, (Cfg<2, 64>::kSmemBytes)));
     FA_CUDA(cudaFuncSetAttribute(k_gemm_tc2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<1>::kSmemBytes));
     FA_CUDA(cudaFuncSetAttribute(k_gemm_tc2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<2>::kSmemBytes));
+    FA_CUDA(cudaFuncSetAttribute((k_gemm_tc2<1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<1>::kSmemBytes));
     FA_CUDA(cudaFuncSetAttribute(k_gemm_tc2_ar, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgAR::kSmemBytes));
     int dev = 0;
     FA_CUDA(cudaGetDevice(&dev));
@@ -949,6 +990,25 @@ TcOperand tc_make_operand(const __nv_bfloat16* base, int rows, int k, int64_t ro
                                 strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) throw Error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+    return op;
+}
+
+TcOperand tc_make_operand_f8(const uint8_t* base, int rows, int k, int64_t row_stride_bytes, int box_rows) {
+    FA_REQUIRE(g_encode != nullptr, "tc_init_device() has not run");
+    FA_REQUIRE(row_stride_bytes % 16 == 0, "TMA strides must be multiples of 16 bytes");
+    FA_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base must be 16-byte aligned");
+    TcOperand op;
+    op.rows = rows; op.k = k; op.planes = 1;
+    const cuuint64_t dims[3] = {(cuuint64_t)k, (cuuint64_t)rows, 1};
+    const cuuint64_t strides[2] = {(cuuint64_t)row_stride_bytes, (cuuint64_t)row_stride_bytes * rows};
+    const cuuint32_t box[3] = {(cuuint32_t)(2 * BK), (cuuint32_t)box_rows, 1};      // 128 e4m3 = 128 bytes
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = g_encode(&op.map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(base), dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw Error("cuTensorMapEncodeTiled (e4m3 operand) failed with code " + std::to_string((int)r));
+    op.map64 = op.map;
+    op.has64 = box_rows == 64;
     return op;
 }
 
@@ -1006,6 +1066,10 @@ void launch_gemm_tc(const TcOperand& a, const TcOperand& w, int m, int n, int k,
     ep.amax_val = e.amax_val; ep.amax_idx = e.amax_idx;
     ep.cand_run_max = e.cand.run_max; ep.cand_count = e.cand.count; ep.cand_list = e.cand.list; ep.cand_bound2 = e.cand.bound2;
     ep.cand_cap = e.cand.cap; ep.gate = e.gate;
+    ep.col_scale = e.col_scale; ep.out_f8 = e.out_f8; ep.ld8 = e.ld8;
+    FA_REQUIRE(!ep.out_f8 || (n % 32 == 0 && e.ld8 % 16 == 0 && (reinterpret_cast<uintptr_t>(ep.out_f8) & 15) == 0),
+               "e4m3 output needs N % 32 == 0 and 16-byte aligned rows");
+    FA_REQUIRE(!ep.col_scale || (reinterpret_cast<uintptr_t>(ep.col_scale) & 15) == 0, "column scales must be 16-byte aligned");
     ep.ldr = e.ldr; ep.ldc = e.ldc; ep.ldp = e.ldp; ep.relu = e.relu ? 1 : 0; ep.n_slots = tc_argmax_tiles(n);
     ep.pl_col_scale = e.pl_col_scale; ep.pl_col_scale_end = e.pl_col_scale_end; ep.f32_col_begin = e.f32_col_begin;
     FA_REQUIRE(e.pl_col_scale_end % 32 == 0 && e.f32_col_begin % 32 == 0, "column ranges of the epilogue must be multiples of 32");
@@ -1044,6 +1108,20 @@ void launch_gemm_tc(const TcOperand& a, const TcOperand& w, int m, int n, int k,
     // CTA pairs (256 x 256 tiles) once there is at least a full wave of them; below that the 128-row
     // tiles of the single-CTA kernel spread a small M over twice as many SMs.
     const int pair_tiles = cdiv(m, 2 * BM) * cdiv(n, BN);
+    if (e.f8) {
+        // e4m3 operands: always the CTA-pair kernel (a short M simply runs fewer pairs)
+        FA_REQUIRE(a.has64 == false && w.has64, "fp8 gemm: A needs 128-row boxes, W 64-row boxes");
+        Sched s{};
+        s.m_tiles = cdiv(m, 2 * BM); s.n_tiles = cdiv(n, BN); s.band = 8;
+        const int pairs = pair_tiles < g_num_pairs ? pair_tiles : g_num_pairs;
+        s.full_units = pair_tiles / pairs * pairs;
+        const int rest = pair_tiles - s.full_units;
+        s.split_log2 = (rest > 0 && 2 * rest <= pairs) ? 1 : 0;
+        s.total_units = s.full_units + (rest << s.split_log2);
+        if (g_prof_on) { char tag[64]; snprintf(tag, sizeof tag, "fp8_n%d_k%d", n, k); prof_note_tag(tag); }
+        FA_LAUNCH((k_gemm_tc2<1, true>), 2 * pairs, kThreads, Cfg2<1>::kSmemBytes, st, a.map, w.map, map_out, map_pl, m, n, k, s, ep);
+        return;
+    }
     const int force = gemm_kernel_override();
     // one-product projections that store nothing (the vocabulary argmax epilogues) and whose K fits: A stays in
     // shared memory, only W streams.  FUNASR_B200_GEMM_AR=0 falls back to the general pair kernel (comparison aid).

@@ -62,7 +62,7 @@ struct Planes {           // bf16 hi/lo planes of an [M][ld] activation; lo may 
 // LN(x[seg_off[b] + t]) for t < t_valid[b] and zero otherwise (rows = batch * frames, t_valid required).
 void launch_layernorm(const float* x, int rows, int d, const float* gamma, const float* beta, float eps,
                       const int* t_valid /*nullable*/, int frames, float* y_f32, Planes y_pl, cudaStream_t st,
-                      const int* seg_off = nullptr);
+                      const int* seg_off = nullptr, uint8_t* y_f8 = nullptr);
 // FSMN memory block: out = (resid ? resid : 0) + depthwise_conv11(v*m) + v*m.   v has row stride ldv.
 // pk != nullptr: packed rows; segment b is rows seg_off[b] .. + t_valid[b] - 1 (`frames` is then ignored).
 void launch_fsmn(const float* v, int ldv, const float* w /*[512][11]*/, const int* t_valid, int batch, int frames,
@@ -73,6 +73,11 @@ void launch_row_keep(const float* in, float* out, int batch, int frames, int d, 
                      const int* seg_off = nullptr);
 // fp32 -> planes
 void launch_split_planes(const float* x, int64_t n, Planes out, cudaStream_t st);
+// fp32 -> e4m3 (round to nearest even, saturating)
+void launch_to_e4m3(const float* x, int64_t n, uint8_t* out, cudaStream_t st);
+// per-output-channel weight quantisation (02-Quantize-ONNX.py:41-44 per_channel=True): scale[r] = max|w[r]| / 448,
+// w8[r] = e4m3(w[r] / scale[r])
+void launch_quant_rows_e4m3(const float* w, int rows, int k, uint8_t* w8, float* scale, cudaStream_t st);
 // ids[r] = first argmax over logits[r][0..n)
 void launch_argmax_rows(const float* logits, int rows, int n, int ld, int32_t* ids, cudaStream_t st);
 // combine per-tile (max, idx) partials written by the fused vocabulary GEMM epilogue
@@ -114,6 +119,12 @@ struct Epilogue {
     VocabCand cand;
     // the whole launch is a no-op when *gate == 0 (read on the device: no host round trip)
     const int32_t* gate = nullptr;
+    // fp8 speed mode (FA_PREC_FP8): operands are e4m3 bytes; the accumulator is multiplied by the per-output-channel
+    // weight scale before the bias, and the output may leave as e4m3 for the next projection
+    bool f8 = false;
+    const float* col_scale = nullptr; // [N]
+    uint8_t* out_f8 = nullptr;        // [M][ld8]
+    int ld8 = 0;
 };
 // C = A[M][K] * W[N][K]^T  in fp32 on the CUDA cores (exact-precision mode and on-device arbiter).
 void launch_gemm_simt(const float* a, int lda, const float* w, int m, int n, int k, const Epilogue& ep, cudaStream_t st);
@@ -128,6 +139,8 @@ struct TcOperand {
 };
 TcOperand tc_make_operand(const __nv_bfloat16* base, int rows, int k, int64_t row_stride_elems, int64_t plane_stride_elems,
                           int planes, int box_rows);
+// e4m3 operand [rows][k] bytes (one plane); box_rows 128 for activations, 64 for weights
+TcOperand tc_make_operand_f8(const uint8_t* base, int rows, int k, int64_t row_stride_bytes, int box_rows);
 // a weight matrix [planes][rows][k], contiguous rows: both box shapes, so either GEMM kernel can read it
 TcOperand tc_make_weight(const __nv_bfloat16* base, int rows, int k, int64_t plane_stride_elems, int planes);
 constexpr int kTcBlockM = 128, kTcBlockN = 256, kTcBlockK = 64;

@@ -24,7 +24,7 @@ k_layernorm(const float* x, int rows, int d, const float* __restrict__ gamma,
             const float* __restrict__ beta, float eps, const int* __restrict__ t_valid, int frames,
             float* y /* may alias x: a warp reads its rows before it writes them */,
             __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo,
-            const int* __restrict__ seg_off /* unpack: x packed, outputs physical */) {
+            const int* __restrict__ seg_off /* unpack: x packed, outputs physical */, uint8_t* __restrict__ y_f8) {
     grid_dependency_wait();
     const int row0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * kLnRows, lane = threadIdx.x & 31;
     if (row0 >= rows) return;
@@ -93,6 +93,7 @@ k_layernorm(const float* x, int rows, int d, const float* __restrict__ gamma,
                 *reinterpret_cast<uint2*>(y_hi + o) = h;
                 if (y_lo) *reinterpret_cast<uint2*>(y_lo + o) = l;
             }
+            if (y_f8) *reinterpret_cast<uint32_t*>(y_f8 + o) = f32x4_to_e4m3(o4.x, o4.y, o4.z, o4.w);
         }
     }
 }
@@ -277,6 +278,36 @@ k_split_planes(const float4* __restrict__ x, int64_t n4, __nv_bfloat16* __restri
     split_bf16x2(v.z, v.w, h.y, l.y);
     *reinterpret_cast<uint2*>(hi + i * 4) = h;
     if (lo) *reinterpret_cast<uint2*>(lo + i * 4) = l;
+}
+
+__global__ void __launch_bounds__(256)
+k_to_e4m3(const float4* __restrict__ x, int64_t n4, uint32_t* __restrict__ out) {
+    grid_dependency_wait();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float4 v = x[i];
+    out[i] = f32x4_to_e4m3(v.x, v.y, v.z, v.w);
+}
+
+// one warp per weight row: scale = max|w| / 448 (1 for an all-zero row), w8 = e4m3(w / scale)
+__global__ void __launch_bounds__(256)
+k_quant_rows_e4m3(const float* __restrict__ w, int rows, int k, uint8_t* __restrict__ w8, float* __restrict__ scale) {
+    grid_dependency_wait();
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* wr = w + (int64_t)row * k;
+    float mx = 0.f;
+    for (int i = lane * 4; i < k; i += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(wr + i);
+        mx = fmaxf(fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    }
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float sc = mx > 0.f ? mx / 448.0f : 1.0f;
+    for (int i = lane * 4; i < k; i += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(wr + i);
+        *reinterpret_cast<uint32_t*>(w8 + (int64_t)row * k + i) = f32x4_to_e4m3(v.x / sc, v.y / sc, v.z / sc, v.w / sc);
+    }
+    if (lane == 0) scale[row] = sc;
 }
 
 // ------------------------------------------------------------------------------------ argmax
@@ -512,22 +543,23 @@ k_ctc_collapse(const int32_t* __restrict__ ids, int frames, int blank, int32_t* 
 }  // namespace
 
 void launch_layernorm(const float* x, int rows, int d, const float* gamma, const float* beta, float eps,
-                      const int* t_valid, int frames, float* y_f32, Planes y_pl, cudaStream_t st, const int* seg_off) {
+                      const int* t_valid, int frames, float* y_f32, Planes y_pl, cudaStream_t st, const int* seg_off,
+                      uint8_t* y_f8) {
     FA_REQUIRE(d % 4 == 0 && d <= 128 * kLnMaxVec, "layernorm width must be a multiple of 4 and <= 1024");
     FA_REQUIRE(!seg_off || (t_valid && y_f32 != x), "layernorm unpack needs the length vector and an output that is not its input");
     // algorithmic bytes: the row in, and whichever outputs are written (fp32 row, bf16 hi plane, bf16 lo plane)
-    prof_note_work(0.0, (double)rows * d * (4.0 + (y_f32 ? 4.0 : 0.0) + (y_pl.hi ? 2.0 : 0.0) + (y_pl.lo ? 2.0 : 0.0)));
+    prof_note_work(0.0, (double)rows * d * (4.0 + (y_f32 ? 4.0 : 0.0) + (y_pl.hi ? 2.0 : 0.0) + (y_pl.lo ? 2.0 : 0.0) + (y_f8 ? 1.0 : 0.0)));
     // d <= 512 (141 of the 155 launches of a step): one row per warp — 40 registers, 48 resident warps per SM; two rows
     // per warp (62 registers) measured 6 % slower on the same box, four rows 18 % slower
     if (d <= 512) {
-        FA_LAUNCH((k_layernorm<4, 1>), cdiv(rows, 8), 256, 0, st, x, rows, d, gamma, beta, eps, t_valid, frames, y_f32, y_pl.hi, y_pl.lo, seg_off);
+        FA_LAUNCH((k_layernorm<4, 1>), cdiv(rows, 8), 256, 0, st, x, rows, d, gamma, beta, eps, t_valid, frames, y_f32, y_pl.hi, y_pl.lo, seg_off, y_f8);
         return;
     }
     const int grid = cdiv(rows, 8 * 2);
     if (d <= 640) {
-        FA_LAUNCH(k_layernorm<5>, grid, 256, 0, st, x, rows, d, gamma, beta, eps, t_valid, frames, y_f32, y_pl.hi, y_pl.lo, seg_off);
+        FA_LAUNCH(k_layernorm<5>, grid, 256, 0, st, x, rows, d, gamma, beta, eps, t_valid, frames, y_f32, y_pl.hi, y_pl.lo, seg_off, y_f8);
     } else {
-        FA_LAUNCH(k_layernorm<8>, grid, 256, 0, st, x, rows, d, gamma, beta, eps, t_valid, frames, y_f32, y_pl.hi, y_pl.lo, seg_off);
+        FA_LAUNCH(k_layernorm<8>, grid, 256, 0, st, x, rows, d, gamma, beta, eps, t_valid, frames, y_f32, y_pl.hi, y_pl.lo, seg_off, y_f8);
     }
 }
 
@@ -565,6 +597,16 @@ void launch_row_keep(const float* in, float* out, int batch, int frames, int d, 
 void launch_split_planes(const float* x, int64_t n, Planes out, cudaStream_t st) {
     FA_REQUIRE(n % 4 == 0, "split_planes length must be a multiple of 4");
     FA_LAUNCH(k_split_planes, cdiv(n / 4, 256), 256, 0, st, reinterpret_cast<const float4*>(x), n / 4, out.hi, out.lo);
+}
+
+void launch_to_e4m3(const float* x, int64_t n, uint8_t* out, cudaStream_t st) {
+    FA_REQUIRE(n % 4 == 0, "to_e4m3 length must be a multiple of 4");
+    FA_LAUNCH(k_to_e4m3, cdiv(n / 4, 256), 256, 0, st, reinterpret_cast<const float4*>(x), n / 4, reinterpret_cast<uint32_t*>(out));
+}
+
+void launch_quant_rows_e4m3(const float* w, int rows, int k, uint8_t* w8, float* scale, cudaStream_t st) {
+    FA_REQUIRE(k % 4 == 0, "quant_rows needs K % 4 == 0");
+    FA_LAUNCH(k_quant_rows_e4m3, cdiv(rows, 8), 256, 0, st, w, rows, k, w8, scale);
 }
 
 void launch_argmax_rows(const float* logits, int rows, int n, int ld, int32_t* ids, cudaStream_t st) {

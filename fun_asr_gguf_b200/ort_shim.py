@@ -122,12 +122,13 @@ def precision_for(model_path: str) -> str:
     04-Inference.py:42-43 defaults to ``.fp16.onnx``): ``.fp32.`` the traced FP32 graph, ``.fp16.`` everything but
     LayerNorm in half precision, ``.int8.`` per-channel dynamic QUInt8 MatMuls.  Here: the fp32 and fp16
     names run the bf16x3 mode — 16 mantissa bits per operand, i.e. at least the fp16 graph's accuracy and token-exact
-    against the FP32 one — and the int8 name, whose user has asked for speed at ~2^-8 per operand, runs the one-product
-    bf16 mode (same operand precision class, 1.3x the throughput).  ``$FUNASR_B200_PRECISION`` overrides."""
+    against the FP32 one — and the int8 name, whose user has asked for 8-bit MatMuls with per-channel weight scales,
+    runs the fp8 mode (e4m3 x e4m3 on tcgen05 kind::f8f6f4, per-output-channel weight scales, LayerNorm and softmax in
+    fp32 as 02-Quantize-ONNX.py:26 keeps them).  ``$FUNASR_B200_PRECISION`` overrides (fp32, bf16x3, bf16, fp8)."""
     env = os.environ.get("FUNASR_B200_PRECISION")
     if env:
         return env
-    return "bf16" if ".int8." in os.path.basename(model_path).lower() else "bf16x3"
+    return "fp8" if ".int8." in os.path.basename(model_path).lower() else "bf16x3"
 
 
 _tensors: Dict[tuple, "object"] = {}      # checkpoint tensors by key: growing an engine does not re-read the file

@@ -35,7 +35,11 @@ typedef struct fa_ctx fa_ctx;
 enum fa_precision {
     FA_PREC_FP32 = 0,   /* fp32 FMA on the CUDA cores: exact-precision mode and on-device arbiter      */
     FA_PREC_BF16X3 = 1, /* tcgen05, operands as bf16 hi+lo planes, 3 MMAs per product, fp32 accumulate */
-    FA_PREC_BF16 = 2    /* tcgen05, plain bf16 operands, fp32 accumulate (fast mode, not token-exact)  */
+    FA_PREC_BF16 = 2,   /* tcgen05, plain bf16 operands, fp32 accumulate (fast mode, not token-exact)  */
+    FA_PREC_FP8 = 3     /* tcgen05 kind::f8f6f4: e4m3 activations, e4m3 weights with a per-output-channel scale (the
+                           reference's int8 graph variant, 02-Quantize-ONNX.py:41-44, as W8A8 floating point); the
+                           attention products, its output projection, LayerNorm and softmax stay as in FA_PREC_BF16 /
+                           fp32 (02-Quantize-ONNX.py:26).  Speed mode with a stated id-mismatch budget.             */
 };
 
 FA_API int fa_abi_version(void);

@@ -328,3 +328,36 @@ def test_fsmn_streaming_kernel_matches_the_strip_kernel_bit_for_bit(raw, monkeyp
     vm = torch.from_numpy(v).double() * m
     conv = F.conv1d(F.pad(vm.transpose(1, 2), (5, 5)), torch.from_numpy(w).double().unsqueeze(1), groups=512).transpose(1, 2)
     assert rel_err(got, conv + vm + torch.from_numpy(resid).double()) <= 2e-6
+
+
+# ------------------------------------------------------------------------------------ fp8 speed mode
+
+def _e4m3(x: torch.Tensor) -> torch.Tensor:
+    """Round to e4m3 (nearest even, saturating at +-448) and back, on the CPU: what the kernels' conversions do."""
+    return x.clamp(-448.0, 448.0).to(torch.float8_e4m3fn).to(torch.float32)
+
+
+@pytest.mark.parametrize("m,n,k", [(300, 512, 512), (129, 1536, 560), (515, 2048, 512), (1001, 512, 2048), (260, 256, 128),
+                                   (2100, 1024, 256)])
+def test_linear_fp8_is_the_quantised_product(raw, m, n, k):
+    """FA_PREC_FP8 projections: tcgen05 kind::f8f6f4 on e4m3 activations (converted as they are) and e4m3 weights with a
+    per-output-channel scale max|w_row| / 448 (02-Quantize-ONNX.py:41-44, per_channel=True).  The kernel must compute
+    exactly that quantised product — the e4m3 x e4m3 products are exact in fp32, so against a float64 product of the
+    same quantised operands only the fp32 accumulation order is left — with bias, ReLU, residual and the e4m3 output
+    form the next projection reads."""
+    a, w = _rand((m, k), 11), _rand((n, k), 12, k ** -0.5)
+    bias, resid = _rand((n,), 13), _rand((m, n), 14)
+    ta, tw = torch.from_numpy(a), torch.from_numpy(w)
+    scale = tw.abs().amax(1) / 448.0
+    a8, w8 = _e4m3(ta), _e4m3(tw / scale[:, None])
+    ref = (a8.double() @ w8.double().t()) * scale.double() + torch.from_numpy(bias).double()
+    got = raw.linear(a, w, bias, precision="fp8")
+    assert rel_err(got, ref) <= 2e-6
+    # and it is a sane approximation of the fp32 product (3 mantissa bits per operand, K-fold averaging)
+    exact = ta.double() @ tw.double().t() + torch.from_numpy(bias).double()
+    assert rel_err(got, exact) <= 0.08
+    got, out8 = raw.linear(a, w, bias, relu=True, precision="fp8", planes=True)
+    assert rel_err(got, torch.relu(ref)) <= 2e-6
+    assert np.array_equal(out8, _e4m3(torch.from_numpy(got)).numpy())                  # the e4m3 output is the rounding of the fp32 one
+    got = raw.linear(a, w, bias, resid=resid, precision="fp8")
+    assert rel_err(got, ref + torch.from_numpy(resid).double()) <= 2e-6

@@ -125,7 +125,7 @@ def test_model_file_name_selects_the_precision_mode(monkeypatch):
     monkeypatch.delenv("FUNASR_B200_PRECISION", raising=False)
     assert ort_shim.precision_for("m/Fun-ASR-Nano-Encoder-Adaptor.fp32.onnx") == "bf16x3"
     assert ort_shim.precision_for("m/Fun-ASR-Nano-Encoder-Adaptor.fp16.onnx") == "bf16x3"
-    assert ort_shim.precision_for("m/Fun-ASR-Nano-CTC.int8.onnx") == "bf16"
+    assert ort_shim.precision_for("m/Fun-ASR-Nano-CTC.int8.onnx") == "fp8"
     monkeypatch.setenv("FUNASR_B200_PRECISION", "fp32")
     assert ort_shim.precision_for("m/Fun-ASR-Nano-CTC.int8.onnx") == "fp32"
 
