@@ -297,9 +297,7 @@ def run_ours(args) -> None:
     def step(i):
         for a, lens in dev_in[i & 1]:
             b, t = a.shape[0], eng.frames(a.shape[1])
-            e = enc[: b * t * 512].view(b, t, 512)
-            eng.encode_cuda(a, lens, e, ad[: b * t * 1024].view(b, t, 1024))
-            eng.ctc_cuda(e, ids[: b * t].view(b, t))
+            eng.front_half_cuda(a, lens, enc[: b * t * 512].view(b, t, 512), ad[: b * t * 1024].view(b, t, 1024), ids[: b * t].view(b, t))
 
     def fence():
         torch.cuda.synchronize()

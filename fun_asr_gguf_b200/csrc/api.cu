@@ -121,6 +121,14 @@ int fa_front_half(fa_ctx* ctx, const float* audio, int batch, int64_t samples, c
     });
 }
 
+int fa_front_half_dev(fa_ctx* ctx, const float* audio, int batch, int64_t samples, const int64_t* ilens, float* enc,
+                      float* adaptor, int32_t* ids) {
+    return guarded([&] {
+        NEED(ctx); NEED(audio); NEED(ilens); NEED(ids);
+        ctx->impl.front_half_dev(audio, batch, samples, ilens, enc, adaptor, ids);
+    });
+}
+
 int fa_front_half_embd(fa_ctx* ctx, const float* audio, int batch, int64_t samples, const int64_t* ilens, float* enc,
                        float* const* embd_rows, int64_t* rows_out, int32_t* ids) {
     return guarded([&] {

@@ -114,6 +114,7 @@ struct AttnParams {
     const int* seg_off;
     const int* order;
     const int* tile_off;
+    const float* key_bias;                     // [batch] added to the score of each segment's last key (Packing::last_key_bias)
     long long* dbg;                            // tuning aid (FUNASR_B200_ATTN_TIMING): cycles the MMA warp waits, by cause
 };
 
@@ -503,6 +504,14 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, const __grid_constant
                     uint32_t s[32];
                     tc_ld32(ts, s);
                     tc_wait_ld();
+                    if (p.key_bias && j == n - 1 && klen - 1 >= kbase && klen - 1 < kbase + 32) {   // warp-uniform, once per item
+                        // the segment's last key stands for n_pad identical keys: weight n_pad * exp2(s) = exp2(s + log2 n_pad)
+                        const int at = klen - 1 - kbase;
+                        const float kb = p.key_bias[b];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (i == at) s[i] = __float_as_uint(__uint_as_float(s[i]) + kb);
+                    }
                     const bool full_chunk = kbase + 32 <= klen;
                     uint32_t hi[16], lo[16];                         // 32 keys x bf16, packed in pairs (even key in the low half)
 #pragma unroll
@@ -804,7 +813,7 @@ void launch_attention_tc(Planes qkv, int64_t plane_stride, int ld, int d_model, 
     if (ctx_pl.hi && !ctx_f32) map_out = pk ? att_out_map(ctx_pl, ldo, d_model, pk->total_rows, 1) : att_out_map(ctx_pl, ldo, d_model, frames, batch);
     const int items = pk ? heads * pk->total_tiles : batch * heads * cdiv(frames, QT);
     p.items = items;
-    if (pk) { p.seg_off = pk->seg_off; p.order = pk->order; p.tile_off = pk->tile_off; }
+    if (pk) { p.seg_off = pk->seg_off; p.order = pk->order; p.tile_off = pk->tile_off; p.key_bias = pk->last_key_bias; }
     int grid = items < g_att_sms ? items : g_att_sms;
     if (const char* e = getenv("FUNASR_B200_ATT_SMS")) { const int v = atoi(e); if (v > 0 && v < grid) grid = v; }   // tuning aid: fewer CTAs
     // the repeat bitmap holds one bit per item of a CTA's sequence; more would spill into the barriers behind it

@@ -381,7 +381,8 @@ void Context::finalize() {
         logits_rows_ = (int)std::min<size_t>(M, 2048);
         logits_.alloc((size_t)logits_rows_ * vocab_ * 4);
     }
-    len_ints_ = 6 * max_batch_ + 2;              // n_valid, t_valid, target_len, seg_off[B+1], order[B], tile_off[B+1]
+    // n_valid, t_valid, target_len, seg_off[B+1], order[B], tile_off[B+1]; CTC head: seg_off[B+1], tile_off[B+1], len[B], bias[B]
+    len_ints_ = 10 * max_batch_ + 4;
     lens_.alloc((size_t)len_ints_ * sizeof(int));
     d_nvalid_ = lens_.as<int>();
     d_tvalid_ = d_nvalid_ + max_batch_;
@@ -536,9 +537,8 @@ void Context::sanm_layer(const SanmLayer& L, bool first, int batch, int frames) 
     linear(f, L.w2, M, e2);
 }
 
-void Context::projector(const Projector& P, const Act& in, int batch, int frames, const int* kv_len, bool packed) {
-    const int M = packed ? pk_.total_rows : batch * frames, d = P.d;
-    const Packing* pk = packed ? &pk_ : nullptr;
+void Context::projector(const Projector& P, const Act& in, int batch, int frames, const int* kv_len, const Packing* pk) {
+    const int M = pk ? pk->total_rows : batch * frames, d = P.d;
     const bool f32 = prec_ == kFp32;
     float* x = x_.as<float>();
     const Act f = ffn_act(kDffn);
@@ -580,6 +580,10 @@ void Context::stage_lengths(int batch, int64_t s_phys, const int64_t* h_ilens, b
     int* h_off = hl + 3 * max_batch_;            // [B+1]
     int* h_order = h_off + max_batch_ + 1;       // [B]
     int* h_tile = h_order + max_batch_;          // [B+1]
+    int* h_off_c = h_tile + max_batch_ + 1;      // [B+1]  CTC head packing
+    int* h_tile_c = h_off_c + max_batch_ + 1;    // [B+1]
+    int* h_len_c = h_tile_c + max_batch_ + 1;    // [B]
+    float* h_bias_c = reinterpret_cast<float*>(h_len_c + max_batch_);     // [B]
     const int frames = lfr_frames_of(s_phys);
     int total = 0, longest = 0;
     double sq = 0.0;
@@ -609,7 +613,29 @@ void Context::stage_lengths(int batch, int64_t s_phys, const int64_t* h_ilens, b
         pk_.order = pk_.seg_off + max_batch_ + 1;
         pk_.tile_off = pk_.order + max_batch_;
         pk_.total_rows = total; pk_.total_tiles = tiles; pk_.max_len = longest; pk_.sum_len_sq = sq;
+        // the CTC head's rows: valid frames, then one row standing for the segment's frames - t_valid zero-padded frames
+        int total_c = 0, tiles_c = 0;
+        double sq_c = 0.0;
+        for (int b = 0; b < batch; ++b) {
+            const int n_pad = frames - h_tv[b];
+            h_len_c[b] = h_tv[b] + (n_pad > 0 ? 1 : 0);
+            h_bias_c[b] = n_pad > 1 ? std::log2((float)n_pad) : 0.f;
+            h_off_c[b] = total_c;
+            total_c += h_len_c[b];
+            sq_c += (double)h_len_c[b] * h_len_c[b];
+        }
+        h_off_c[batch] = total_c;
+        for (int k = 0; k < batch; ++k) { h_tile_c[k] = tiles_c; tiles_c += cdiv(h_len_c[h_order[k]], 128); }
+        h_tile_c[batch] = tiles_c;
+        pk_ctc_ = Packing{};
+        pk_ctc_.order = pk_.order;
+        pk_ctc_.seg_off = pk_.tile_off + max_batch_ + 1;
+        pk_ctc_.tile_off = pk_ctc_.seg_off + max_batch_ + 1;
+        d_len_ctc_ = pk_ctc_.tile_off + max_batch_ + 1;
+        pk_ctc_.last_key_bias = reinterpret_cast<const float*>(d_len_ctc_ + max_batch_);
+        pk_ctc_.total_rows = total_c; pk_ctc_.total_tiles = tiles_c; pk_ctc_.max_len = longest + 1; pk_ctc_.sum_len_sq = sq_c;
     }
+    ctc_packed_ready_ = false;
     FA_CUDA(cudaMemcpyAsync(lens_.p, hl, (size_t)len_ints_ * sizeof(int), cudaMemcpyHostToDevice, stream_));
     FA_CUDA(cudaEventRecord(len_ev_[slot], stream_));
 }
@@ -677,7 +703,17 @@ void Context::encoder_graph(int batch, int64_t s_phys, float* d_enc, float* d_ad
     }
     if (record_events) FA_CUDA(cudaEventRecord(ev_enc_, stream_));       // enc_output is final: a download may start
 
-    projector(adaptor_, in, batch, frames, d_tvalid_, pk != nullptr);
+    if (pk && fused_ctc_next_) {
+        // the CTC head's input, in its own packing, before the adaptor reuses the buffer `in` lives in
+        const Act c = ctc_packed_input();
+        if (f8) launch_repack_rows(in.f8, c.f8, kDenc, pk->seg_off, pk_ctc_.seg_off, d_tvalid_, batch, pk->max_len, stream_);
+        else {
+            launch_repack_rows(in.pl.hi, c.pl.hi, kDenc * 2, pk->seg_off, pk_ctc_.seg_off, d_tvalid_, batch, pk->max_len, stream_);
+            launch_repack_rows(in.pl.lo, c.pl.lo, kDenc * 2, pk->seg_off, pk_ctc_.seg_off, d_tvalid_, batch, pk->max_len, stream_);
+        }
+        ctc_packed_ready_ = true;
+    }
+    projector(adaptor_, in, batch, frames, d_tvalid_, pk);
     launch_row_keep(x, d_adaptor, batch, frames, kDllm, d_tlen_, stream_, seg_off);
     if (record_events) FA_CUDA(cudaEventRecord(ev_ad_, stream_));
 }
@@ -721,35 +757,73 @@ void Context::run_graphed(int kind, int batch, int64_t size, F&& body) {
 }
 
 
+Act Context::ctc_packed_input() const {
+    Act a; a.ld = kDenc;
+    a.pl = Planes{encpl_.as<__nv_bfloat16>(), encpl_.as<__nv_bfloat16>() + m_max_ * kDenc};
+    a.f8 = enc8_.as<uint8_t>();
+    return a;
+}
+
 void Context::ctc_dev(const float* d_enc, int batch, int frames, int32_t* d_ids) {
     FA_REQUIRE(finalized_, "context not finalized");
     FA_REQUIRE(batch >= 1 && batch <= max_batch_ && frames >= 1 && frames <= t_max_, "CTC input exceeds the context's capacity");
     set_device();
     const int M = batch * frames;
-    const bool f32 = prec_ == kFp32;
     Act in; in.f32 = d_enc; in.ld = kDenc;
     if (prec_ == kFp8) {
         in.f8 = enc8_.as<uint8_t>();
         launch_to_e4m3(d_enc, (int64_t)M * kDenc, in.f8, stream_);
-    } else if (!f32) {
+    } else if (prec_ != kFp32) {
         in.pl = Planes{encpl_.as<__nv_bfloat16>(), encpl_.as<__nv_bfloat16>() + m_max_ * kDenc};
         launch_split_planes(d_enc, (int64_t)M * kDenc, in.pl, stream_);
     }
-    projector(ctc_, in, batch, frames, nullptr, false);
+    ctc_graph(in, batch, frames, d_ids, nullptr);
+}
+
+// The head in the same call as the encoder: a packed batch keeps the head's packing (one row per segment for all its
+// zero-padded frames, whose key counts n_pad times); otherwise the physical rows of d_enc.
+void Context::ctc_after_encoder(const float* d_enc, int batch, int frames, int32_t* d_ids) {
+    if (packed_ && ctc_packed_ready_) {
+        ctc_graph(ctc_packed_input(), batch, frames, d_ids, &pk_ctc_);
+        return;
+    }
+    ctc_dev(d_enc, batch, frames, d_ids);
+}
+
+void Context::ctc_graph(const Act& in, int batch, int frames, int32_t* d_ids, const Packing* pk) {
+    const int M = pk ? pk->total_rows : batch * frames;
+    const bool f32 = prec_ == kFp32;
+    projector(ctc_, in, batch, frames, pk ? d_len_ctc_ : nullptr, pk);
     float* x = x_.as<float>();
     tap("ctc_h", x, M, kDenc);
+    int32_t* ids_rows = pk ? tokens_.as<int32_t>() : d_ids;           // packed rows -> scratch, then unpacked
     if (f32) {
         for (int r0 = 0; r0 < M; r0 += logits_rows_) {
             const int rows = std::min(logits_rows_, M - r0);
             Epilogue e;
             e.bias = ctc_lo_.b; e.out_f32 = logits_.as<float>(); e.ldc = vocab_;
             launch_gemm_simt(x + (size_t)r0 * kDenc, kDenc, ctc_lo_.w, rows, vocab_, kDenc, e, stream_);
-            launch_argmax_rows(logits_.as<float>(), rows, vocab_, vocab_, d_ids + r0, stream_);
+            launch_argmax_rows(logits_.as<float>(), rows, vocab_, vocab_, ids_rows + r0, stream_);
         }
     } else {
         vocab_argmax(x, h_act(kDenc).pl, ctc_lo_, vocab_wnorm_, M, vocab_rescore_ ? cand_workspace() : VocabCand{},
-                     amax_val_.as<float>(), amax_idx_.as<int32_t>(), d_ids);
+                     amax_val_.as<float>(), amax_idx_.as<int32_t>(), ids_rows);
     }
+    if (pk) launch_unpack_ids(ids_rows, d_ids, batch, frames, pk->seg_off, d_tvalid_, stream_);
+}
+
+void Context::front_half_dev(const float* d_audio, int batch, int64_t s_phys, const int64_t* h_ilens, float* d_enc,
+                             float* d_adaptor, int32_t* d_ids) {
+    ensure_room(batch, s_phys);
+    set_device();
+    if (!d_enc) d_enc = enc_.as<float>();
+    if (!d_adaptor) d_adaptor = adaptor_out_.as<float>();
+    stage_lengths(batch, s_phys, h_ilens, true);
+    front_end(d_audio, 0, batch, s_phys);
+    fused_ctc_next_ = true;
+    try { encoder_graph(batch, s_phys, d_enc, d_adaptor); } catch (...) { fused_ctc_next_ = false; throw; }
+    fused_ctc_next_ = false;
+    ctc_after_encoder(d_enc, batch, lfr_frames_of(s_phys), d_ids);
 }
 
 VocabCand Context::cand_workspace() const {
@@ -884,12 +958,14 @@ void Context::front_half_host(const float* audio, int batch, int64_t s_phys, con
             continue;
         }
         upload_and_front_end(audio + (size_t)b0 * s_phys, nb, s_phys);
-        encoder_graph(nb, s_phys, enc_.as<float>(), adaptor_out_.as<float>());
+        fused_ctc_next_ = ids != nullptr;
+        try { encoder_graph(nb, s_phys, enc_.as<float>(), adaptor_out_.as<float>()); } catch (...) { fused_ctc_next_ = false; throw; }
+        fused_ctc_next_ = false;
         if (enc) download_async(enc + (size_t)b0 * frames * kDenc, enc_.p, (size_t)nb * frames * kDenc * 4, ev_enc_);
         if (adaptor) download_async(adaptor + (size_t)b0 * frames * kDllm, adaptor_out_.p, (size_t)nb * frames * kDllm * 4, ev_ad_);
         if (embd_rows) { FA_CUDA(cudaStreamWaitEvent(copy_stream_, ev_ad_, 0)); hand_off(b0, nb, copy_stream_); }
         if (ids) {
-            ctc_dev(enc_.as<float>(), nb, frames, ids_.as<int32_t>());
+            ctc_after_encoder(enc_.as<float>(), nb, frames, ids_.as<int32_t>());
             FA_CUDA(cudaMemcpyAsync(ids + (size_t)b0 * frames, ids_.p, (size_t)nb * frames * 4, cudaMemcpyDeviceToHost, stream_));
         }
         FA_CUDA(cudaStreamSynchronize(stream_));

@@ -76,6 +76,9 @@ public:
     void encode_dev(const float* d_audio, int batch, int64_t s_phys, const int64_t* h_ilens, float* d_enc,
                     float* d_adaptor);
     void ctc_dev(const float* d_enc, int batch, int frames, int32_t* d_ids);
+    // both graphs back to back on device pointers (d_enc / d_adaptor may be null: the context's own buffers are used)
+    void front_half_dev(const float* d_audio, int batch, int64_t s_phys, const int64_t* h_ilens, float* d_enc, float* d_adaptor,
+                        int32_t* d_ids);
     void collapse_dev(const int32_t* d_ids, int batch, int frames, int32_t* d_tokens, int32_t* d_starts,
                       int32_t* d_counts);
     // host-pointer executions (copies inside); synchronous
@@ -116,7 +119,11 @@ private:
     void attention(const float* qkv, int ld, int d_model, int batch, int frames, int heads, const int* kv_len,
                    float* ctx_f32, Planes ctx_pl, int ldo, const Packing* pk = nullptr);
     void sanm_layer(const SanmLayer& L, bool first, int batch, int frames);
-    void projector(const Projector& P, const Act& in, int batch, int frames, const int* kv_len, bool packed);
+    void projector(const Projector& P, const Act& in, int batch, int frames, const int* kv_len, const Packing* pk);
+    // the CTC head on `in` (uniform rows, or the head's packed rows when pk is given) -> ids of every physical frame
+    void ctc_graph(const Act& in, int batch, int frames, int32_t* d_ids, const Packing* pk);
+    // the CTC head right after encoder_graph in the same call: packed batches keep their packing (SURVEY §7 hard part 2)
+    void ctc_after_encoder(const float* d_enc, int batch, int frames, int32_t* d_ids);
     // LayerNorm into the form the next projection reads at this precision (fp32 / bf16 planes / e4m3)
     void layernorm_to(const float* x, int rows, int d, const float* g, const float* b, float eps, const Act& dst);
     void tap(const char* name, const float* d, int64_t rows, int64_t cols);
@@ -175,8 +182,13 @@ private:
     // Padding-free execution of the encoder and the adaptor (kernels.h Packing): chosen per call by stage_lengths when
     // the batch holds padded frames and is not replayed as a CUDA graph (a graph's launch geometry is fixed)
     bool packed_ = false, allow_packed_env_ = true;
-    Packing pk_;
-    int len_ints_ = 0;           // ints per staging slot: 3 length vectors + seg_off, order, tile_off
+    Packing pk_;                 // encoder + adaptor rows
+    Packing pk_ctc_;             // CTC head rows: the valid frames of a segment plus ONE row for all its padded frames
+    const int* d_len_ctc_ = nullptr;          // [batch] rows of each segment in the head's packing
+    bool fused_ctc_next_ = false;             // the CTC head follows in this call: encoder_graph prepares its packed input
+    Act ctc_packed_input() const;
+    bool ctc_packed_ready_ = false;           // encoder_graph left the head's packed input in encpl_ / enc8_
+    int len_ints_ = 0;           // ints per staging slot: 3 length vectors + seg_off, order, tile_off (+ the head's tables)
     const Packing* packing() const { return packed_ ? &pk_ : nullptr; }
     int enc_rows(int batch, int frames) const { return packed_ ? pk_.total_rows : batch * frames; }
     static constexpr int kLenSlots = 4;       // ring of staging slots: a slot is reused once its upload has completed

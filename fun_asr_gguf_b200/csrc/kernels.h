@@ -22,6 +22,10 @@ struct Packing {
     const int* tile_off = nullptr;   // [batch + 1] prefix sums of 128-query tiles, in `order`
     int total_rows = 0, total_tiles = 0, max_len = 0;
     double sum_len_sq = 0.0;         // sum of t_valid^2: attention FLOP accounting
+    // CTC head only (SURVEY §7 hard part 2): [batch] log2 of the multiplicity of each segment's LAST key.  The head is
+    // unmasked over every physical frame (F7) and all zero-padded frames of a segment are identical rows through every
+    // layer, so they are carried as ONE row whose key counts n_pad times: exp2(s + log2 n_pad) = n_pad * exp2(s).
+    const float* last_key_bias = nullptr;
 };
 
 // ---------------------------------------------------------------- front end (§8a a1-a4)
@@ -71,6 +75,12 @@ void launch_fsmn(const float* v, int ldv, const float* w /*[512][11]*/, const in
 // seg_off != nullptr: `in` is packed (row (b, t) read from seg_off[b] + t), `out` physical
 void launch_row_keep(const float* in, float* out, int batch, int frames, int d, const int* keep, cudaStream_t st,
                      const int* seg_off = nullptr);
+// CTC-head packing: copy rows of `row_bytes` bytes from the encoder's packed layout (segment b at src_off[b], tv[b] rows)
+// to the head's (segment b at dst_off[b], tv[b] rows followed by one all-zero row if the segment has padded frames)
+void launch_repack_rows(const void* src, void* dst, int row_bytes, const int* src_off, const int* dst_off, const int* tv,
+                        int batch, int max_len, cudaStream_t st);
+// ids of the head's packed rows -> physical [batch][frames]: frame t >= tv[b] takes the id of the segment's pad row
+void launch_unpack_ids(const int32_t* packed, int32_t* ids, int batch, int frames, const int* off, const int* tv, cudaStream_t st);
 // fp32 -> planes
 void launch_split_planes(const float* x, int64_t n, Planes out, cudaStream_t st);
 // fp32 -> e4m3 (round to nearest even, saturating)

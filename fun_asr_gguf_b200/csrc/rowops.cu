@@ -267,6 +267,28 @@ k_row_keep(const float4* __restrict__ in, float4* __restrict__ out, int frames, 
     out[i] = t < keep[b] ? in[src] : make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
+__global__ void __launch_bounds__(128)
+k_repack_rows(const uint4* __restrict__ src, uint4* __restrict__ dst, int row16, const int* __restrict__ src_off,
+              const int* __restrict__ dst_off, const int* __restrict__ tv) {
+    grid_dependency_wait();
+    const int t = blockIdx.x, b = blockIdx.y;
+    const int n = tv[b], rows = dst_off[b + 1] - dst_off[b];      // rows = n, or n + 1 with the pad row
+    if (t >= rows) return;
+    uint4* d = dst + ((int64_t)dst_off[b] + t) * row16;
+    const uint4* s = src + ((int64_t)src_off[b] + t) * row16;
+    for (int i = threadIdx.x; i < row16; i += blockDim.x) d[i] = t < n ? s[i] : make_uint4(0u, 0u, 0u, 0u);
+}
+
+__global__ void __launch_bounds__(256)
+k_unpack_ids(const int32_t* __restrict__ packed, int32_t* __restrict__ ids, int frames, const int* __restrict__ off,
+             const int* __restrict__ tv) {
+    grid_dependency_wait();
+    const int b = blockIdx.y, t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= frames) return;
+    const int n = tv[b];
+    ids[(int64_t)b * frames + t] = packed[off[b] + (t < n ? t : n)];
+}
+
 __global__ void __launch_bounds__(256)
 k_split_planes(const float4* __restrict__ x, int64_t n4, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
     grid_dependency_wait();
@@ -592,6 +614,17 @@ void launch_row_keep(const float* in, float* out, int batch, int frames, int d, 
     const int64_t total4 = (int64_t)batch * frames * d / 4;
     FA_LAUNCH(k_row_keep, cdiv(total4, 256), 256, 0, st, reinterpret_cast<const float4*>(in),
               reinterpret_cast<float4*>(out), frames, d / 4, keep, total4, seg_off);
+}
+
+void launch_repack_rows(const void* src, void* dst, int row_bytes, const int* src_off, const int* dst_off, const int* tv,
+                        int batch, int max_len, cudaStream_t st) {
+    FA_REQUIRE(row_bytes % 16 == 0, "repack_rows needs rows of whole 16-byte words");
+    FA_LAUNCH(k_repack_rows, dim3(max_len + 1, batch), 128, 0, st, reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst),
+              row_bytes / 16, src_off, dst_off, tv);
+}
+
+void launch_unpack_ids(const int32_t* packed, int32_t* ids, int batch, int frames, const int* off, const int* tv, cudaStream_t st) {
+    FA_LAUNCH(k_unpack_ids, dim3(cdiv(frames, 256), batch), 256, 0, st, packed, ids, frames, off, tv);
 }
 
 void launch_split_planes(const float* x, int64_t n, Planes out, cudaStream_t st) {

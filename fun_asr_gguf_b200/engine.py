@@ -176,6 +176,23 @@ class FrontHalf:
         _lib.check(self.lib.fa_ctc_dev(self._h, C.c_void_p(enc.data_ptr()), b, t, C.c_void_p(ids.data_ptr())))
         return ids
 
+    def front_half_cuda(self, audio, ilens: Sequence[int], enc=None, adaptor=None, ids=None):
+        """Both graphs back to back on CUDA tensors (fa_front_half_dev); asynchronous on the context's stream.  Mixed-length
+        batches stay padding-free through the CTC head as well.  Returns (enc, adaptor, ids)."""
+        import torch
+        assert audio.is_cuda and audio.dtype == torch.float32 and audio.is_contiguous() and audio.dim() == 2
+        b, s = audio.shape
+        t = self.frames(s)
+        if enc is None:
+            enc = torch.empty((b, t, W.D_ENC), dtype=torch.float32, device=audio.device)
+        if adaptor is None:
+            adaptor = torch.empty((b, t, W.D_LLM), dtype=torch.float32, device=audio.device)
+        if ids is None:
+            ids = torch.empty((b, t), dtype=torch.int32, device=audio.device)
+        _lib.check(self.lib.fa_front_half_dev(self._h, C.c_void_p(audio.data_ptr()), b, s, self._ilens(ilens, b),
+                                              C.c_void_p(enc.data_ptr()), C.c_void_p(adaptor.data_ptr()), C.c_void_p(ids.data_ptr())))
+        return enc, adaptor, ids
+
     def collapse_cuda(self, ids):
         """ids [B][T] int32 CUDA -> (tokens [B][T], start_frames [B][T], counts [B]); nano_ctc.py:70-99."""
         import torch

@@ -89,6 +89,12 @@ FA_API int fa_ctc_dev(fa_ctx* ctx, const float* enc_dev, int batch, int frames, 
 FA_API int fa_front_half(fa_ctx* ctx, const float* audio_host, int batch, int64_t samples, const int64_t* ilens,
                   float* enc_host, float* adaptor_host, int32_t* ids_host);
 
+/* the same on device pointers, asynchronous on the context's stream (enc_dev / adaptor_dev may be NULL: the results then
+ * stay in the context).  Calling the two graphs in ONE entry point lets a mixed-length batch keep its padding-free row
+ * layout through the CTC head as well (one row per segment stands for all its zero-padded frames). */
+FA_API int fa_front_half_dev(fa_ctx* ctx, const float* audio_dev, int batch, int64_t samples, const int64_t* ilens_host,
+                      float* enc_dev, float* adaptor_dev, int32_t* ids_dev);
+
 /* ---- embedding handoff ----------------------------------------------------------------
  * fa_front_half, except that of each segment's adaptor_output only the rows the LLM reads — [0, target_len), what
  * nano_onnx.py:131-133 slices out — leave the device, written straight to embd_rows[b] (host or device memory,

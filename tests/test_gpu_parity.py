@@ -513,7 +513,10 @@ def test_benchmarked_batch_all_rows_match_oracle_and_reference_pins(weights, pla
 # no accuracy statement about them.  Here the speed modes state theirs and this test enforces it: share of frames whose
 # greedy id differs from the FP32 oracle's, and the relative error of enc_output, over the parity signals with the planted
 # CTC projection (ids change every few frames; margins down to 1e-5).  Budgets are ~2x what a B200 measured.
-SPEED_MODE_BUDGET = {"bf16": {"id_mismatch": 0.03, "enc_rel": 0.02}, "fp8": {"id_mismatch": 0.25, "enc_rel": 0.25}}
+# Measured (B200): bf16 14/586 frames = 2.4 %, enc 0.74 %; fp8 136/586 = 23 %, enc 9.9 % — the planted projection is a
+# worst case on purpose (random-init weights, near-tie margins); with plain random init the fp8 mode differs on
+# 52 of 12 012 frames (0.4 %) of the benchmark batch (bench.py --precision fp8, `parity`).
+SPEED_MODE_BUDGET = {"bf16": {"id_mismatch": 0.05, "enc_rel": 0.015}, "fp8": {"id_mismatch": 0.35, "enc_rel": 0.2}}
 
 
 @pytest.mark.parametrize("mode", ["bf16", "fp8"])
