@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfunasr_b200.so")
+# $FUNASR_B200_LIB: another build of the same sources (tuning aid for same-box A/Bs: tools/_ab/*.so)
+LIB_PATH = os.environ.get("FUNASR_B200_LIB") or os.path.join(HERE, "libfunasr_b200.so")
 
 PREC = {"fp32": 0, "bf16x3": 1, "bf16": 2, "fp8": 3}
 

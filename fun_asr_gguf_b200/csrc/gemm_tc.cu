@@ -87,7 +87,14 @@ struct EpiParams {
     int ldr, ldc, ldp, relu, n_slots;            // n_slots: 128-column groups of N (fused argmax partials)
     float pl_col_scale;
     int pl_col_scale_end, f32_col_begin;
+    long long* dbg;                              // tuning aid (-DFA_GEMM_TIMING, FUNASR_B200_GEMM_TIMING=1): per-phase cycles
 };
+
+#ifdef FA_GEMM_TIMING
+#define FA_GT(...) __VA_ARGS__
+#else
+#define FA_GT(...)
+#endif
 
 // K-major operand tile in shared memory, 128-byte rows, SWIZZLE_128B: 8-row groups 1024 B apart.
 // Field layout as in cute::UMMA::SmemDescriptor (start>>4 @0, LBO>>4 @16, SBO>>4 @32, version=1 @46, layout @61).
@@ -155,9 +162,11 @@ __device__ __forceinline__ void epilogue_unit(const EpiParams& ep, const CUtenso
         }
     };
     float4 rv[8], rv_next[8];
+    FA_GT(long long gt[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long g0 = clock64(); long long g1;)
     load_resid(half * 4, rv);
     mbar_wait(bar_ready, ready_parity);                          // the accumulator is complete
     tc_fence_after();
+    FA_GT(g1 = clock64(); gt[0] += g1 - g0; g0 = g1;)
 #pragma unroll 1
     for (int cc = 0; cc < 4; ++cc) {
         const int c = half * 4 + cc;
@@ -178,8 +187,10 @@ __device__ __forceinline__ void epilogue_unit(const EpiParams& ep, const CUtenso
             for (int j = 0; j < 32; ++j) bias[j] = col0 + j < n ? __ldg(ep.bias + col0 + j) : 0.f;
         }
         uint32_t r[32];
+        FA_GT(g1 = clock64(); gt[1] += g1 - g0; g0 = g1;)        // resid request + bias loads
         tc_ld32(taddr + c * 32, r);
         tc_wait_ld();
+        FA_GT(g1 = clock64(); gt[2] += g1 - g0; g0 = g1;)        // TMEM load
         if (ep.col_scale) {                                     // warp-uniform
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -228,7 +239,9 @@ __device__ __forceinline__ void epilogue_unit(const EpiParams& ep, const CUtenso
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
         }
         if (ep.resid) {
+            FA_GT(g1 = clock64(); gt[3] += g1 - g0; g0 = g1;)    // bias add etc.
             stg_acquire();
+            FA_GT(g1 = clock64(); gt[4] += g1 - g0; g0 = g1;)    // wait: previous store has read the staging tile
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int rr = sub + 4 * i;
@@ -244,6 +257,7 @@ __device__ __forceinline__ void epilogue_unit(const EpiParams& ep, const CUtenso
                 v[4 * j + 3] = __fadd_rn(t.w, v[4 * j + 3]);
             }
             __syncwarp();
+            FA_GT(g1 = clock64(); gt[5] += g1 - g0; g0 = g1;)    // residual through the staging tile (incl. waiting for its loads)
         }
         // Outputs leave through the staging tile as tensor stores: the tile is written in the layout the tensor
         // map's swizzle mode expects (128-byte rows / SWIZZLE_128B for fp32, 64-byte rows / SWIZZLE_64B for a
@@ -251,6 +265,7 @@ __device__ __forceinline__ void epilogue_unit(const EpiParams& ep, const CUtenso
         // rows or columns past the matrix edge are clipped by the map.
         if (ep.out && col0 >= ep.f32_col_begin) {
             stg_acquire();
+            FA_GT(g1 = clock64(); gt[4] += g1 - g0; g0 = g1;)
 #pragma unroll
             for (int j = 0; j < 8; ++j)
                 *reinterpret_cast<float4*>(stg + lane * 128 + ((j ^ (lane & 7)) * 16)) =
@@ -262,6 +277,7 @@ __device__ __forceinline__ void epilogue_unit(const EpiParams& ep, const CUtenso
                 bulk_commit();
             }
             store_pending = true;
+            FA_GT(g1 = clock64(); gt[6] += g1 - g0; g0 = g1;)    // fp32 store: smem write, fence, issue
         }
         if (ep.out_f8) {
             // e4m3 (round to nearest even, saturating at +-448): a thread owns 32 consecutive bytes of its row, one sector
@@ -298,10 +314,13 @@ __device__ __forceinline__ void epilogue_unit(const EpiParams& ep, const CUtenso
                 bulk_commit();
             }
             store_pending = true;
+            FA_GT(g1 = clock64(); gt[7] += g1 - g0; g0 = g1;)    // plane store: split, (acquire), smem write, fence, issue
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) rv[i] = rv_next[i];
     }
+    FA_GT(if (ep.dbg && lane == 0) { for (int i = 0; i < 8; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(ep.dbg) + i, (unsigned long long)gt[i]);
+                                      atomicAdd(reinterpret_cast<unsigned long long*>(ep.dbg) + 8, 1ull); })
     if (ep.cand_list && any && row < m) atomicMax(ep.cand_run_max + row, f2ord_dev(best));
     if (ep.amax_val && half * 128 < nw) {
         // one partial slot per (row, 128-column group): the two column halves of a 256-wide tile live in
@@ -616,11 +635,16 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                 const uint32_t idesc = (1u << 4) | (F8 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(nw >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
+                FA_GT(long long m0 = clock64();)
                 mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);       // both CTAs' epilogues have drained this accumulator
+                FA_GT(if (ep.dbg && lane == 0) { atomicAdd(reinterpret_cast<unsigned long long*>(ep.dbg) + 9, (unsigned long long)(clock64() - m0));
+                                                  atomicAdd(reinterpret_cast<unsigned long long*>(ep.dbg) + 10, 1ull); })
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * BN;
                 for (int kb = 0; kb < k_blocks; ++kb) {
+                    FA_GT(long long f0 = clock64();)
                     mbar_wait(bar_full + 8 * stage, phase);
+                    FA_GT(if (ep.dbg && lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(ep.dbg) + 11, (unsigned long long)(clock64() - f0));)
                     tc_fence_after();
                     const uint32_t sbase = tiles_base + stage * C::kStageBytes;
                     const uint32_t a_hi = sbase, a_lo = sbase + kATileBytes;
@@ -1067,6 +1091,29 @@ void launch_gemm_tc(const TcOperand& a, const TcOperand& w, int m, int n, int k,
     ep.cand_run_max = e.cand.run_max; ep.cand_count = e.cand.count; ep.cand_list = e.cand.list; ep.cand_bound2 = e.cand.bound2;
     ep.cand_cap = e.cand.cap; ep.gate = e.gate;
     ep.col_scale = e.col_scale; ep.out_f8 = e.out_f8; ep.ld8 = e.ld8;
+#ifdef FA_GEMM_TIMING
+    struct DbgGuard {
+        long long* d = nullptr; cudaStream_t st; int m, n, k, np; bool resid;
+        ~DbgGuard() {
+            if (!d) return;
+            unsigned long long h[12];
+            cudaStreamSynchronize(st);
+            cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost);
+            cudaFree(d);
+            const double u = h[8] ? (double)h[8] : 1.0;
+            fprintf(stderr, "gemm timing m=%d n=%d k=%d planes=%d resid=%d: per epilogue-warp tile (cycles): wait_acc %.0f | req+bias %.0f tmem_ld %.0f "
+                            "arith %.0f acquire %.0f resid_stage %.0f f32_store %.0f plane_store %.0f | MMA warp per tile: wait_drained %.0f wait_operands %.0f\n",
+                    m, n, k, np, (int)resid, h[0] / u, h[1] / u, h[2] / u, h[3] / u, h[4] / u, h[5] / u, h[6] / u, h[7] / u,
+                    h[10] ? (double)h[9] / h[10] : 0.0, h[10] ? (double)h[11] / h[10] : 0.0);
+        }
+    } dbg_guard;
+    if (getenv("FUNASR_B200_GEMM_TIMING")) {
+        FA_CUDA(cudaMalloc(&dbg_guard.d, 12 * sizeof(long long)));
+        FA_CUDA(cudaMemsetAsync(dbg_guard.d, 0, 12 * sizeof(long long), st));
+        dbg_guard.st = st; dbg_guard.m = m; dbg_guard.n = n; dbg_guard.k = k; dbg_guard.np = e.f8 ? 0 : n_planes; dbg_guard.resid = e.resid != nullptr;
+        ep.dbg = dbg_guard.d;
+    }
+#endif
     FA_REQUIRE(!ep.out_f8 || (n % 32 == 0 && e.ld8 % 16 == 0 && (reinterpret_cast<uintptr_t>(ep.out_f8) & 15) == 0),
                "e4m3 output needs N % 32 == 0 and 16-byte aligned rows");
     FA_REQUIRE(!ep.col_scale || (reinterpret_cast<uintptr_t>(ep.col_scale) & 15) == 0, "column scales must be 16-byte aligned");
@@ -1146,7 +1193,8 @@ void launch_gemm_tc(const TcOperand& a, const TcOperand& w, int m, int n, int k,
     if (w.has64 && force != 1 && (force == 2 || pair_tiles >= g_num_pairs)) {
         Sched s{};
         s.m_tiles = cdiv(m, 2 * BM); s.n_tiles = cdiv(n, BN); s.band = 8;
-        const int pairs = pair_tiles < g_num_pairs ? pair_tiles : g_num_pairs;
+        int pairs = pair_tiles < g_num_pairs ? pair_tiles : g_num_pairs;
+        if (const char* pe = getenv("FUNASR_B200_GEMM_PAIRS")) { const int v = atoi(pe); if (v > 0 && v < pairs) pairs = v; }   // tuning aid
         s.full_units = pair_tiles / pairs * pairs;
         const int rest = pair_tiles - s.full_units;
         s.split_log2 = (rest > 0 && 2 * rest <= pairs) ? 1 : 0;      // a last wave at most half full is cut into half tiles
