@@ -362,8 +362,10 @@ def run_ours(args) -> None:
                 for k, n in enumerate(lens):
                     dst[k] = h_embd.data_ptr() + off * 1024 * 4
                     off += eng.target_len(n)
-                _lib.check(eng.lib.fa_front_half_embd(eng._h, C.c_void_p(h.data_ptr()), b, s, arr, C.c_void_p(h_enc.data_ptr()),
-                                                      dst, None, C.c_void_p(h_ids.data_ptr())))
+                # what a batched caller of the reference's decode step needs: the LLM embeddings and the CTC ids (enc_output
+                # only ever feeds the CTC session, which has already run inside this call)
+                _lib.check(eng.lib.fa_front_half_embd(eng._h, C.c_void_p(h.data_ptr()), b, s, arr, None, dst, None,
+                                                      C.c_void_p(h_ids.data_ptr())))
 
     def time_e2e(compact):
         e2e_step(0, compact)
@@ -380,8 +382,36 @@ def run_ours(args) -> None:
     e2e_value, e2e_compact_value = audio_s_total / e2e_s, audio_s_total / e2e_compact_s
     h2d = sum(h.numel() * 4 for h, _ in P0.batches)
     d2h = sum(h.shape[0] * eng.frames(h.shape[1]) * (512 + 1024 + 1) * 4 for h, _ in P0.batches)
-    d2h_compact = sum(h.shape[0] * eng.frames(h.shape[1]) * (512 + 1) * 4 + sum(eng.target_len(n) for n in lens) * 4096
-                      for h, lens in P0.batches)
+    d2h_compact = sum(h.shape[0] * eng.frames(h.shape[1]) * 4 + sum(eng.target_len(n) for n in lens) * 4096 for h, lens in P0.batches)
+
+    # ---- what the host link gives each rank while ALL ranks copy at once (the e2e limiter at N = 8): the step's own
+    # buffers, host -> device and device -> host, timed alone with CUDA events
+    def copy_rate(dst, src, reps=3):
+        fence()
+        a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            dst.copy_(src, non_blocking=True)
+        b2.record()
+        torch.cuda.synchronize()
+        return src.numel() * src.element_size() * reps / (a.elapsed_time(b2) * 1e-3) / 1e9
+
+    h0 = P0.batches[0][0]
+    d_probe = torch.empty_like(h0, device=dev)
+    h2d_gbs = copy_rate(d_probe, h0)
+    n_probe = min(h_ad.numel(), ad.numel())
+    d2h_gbs = copy_rate(h_ad[:n_probe], ad[:n_probe])
+    rates = torch.tensor([h2d_gbs, d2h_gbs, -h2d_gbs, -d2h_gbs], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(rates, op=dist.ReduceOp.MAX)
+    h2d_max, d2h_max, h2d_min, d2h_min = rates[0].item(), rates[1].item(), -rates[2].item(), -rates[3].item()
+    copy_breakdown = {
+        "h2d_gbs_per_rank": [h2d_min, h2d_max], "d2h_gbs_per_rank": [d2h_min, d2h_max],
+        "h2d_ms_per_step_slowest_rank": h2d / h2d_min / 1e6, "d2h_ms_per_step_slowest_rank": d2h / d2h_min / 1e6,
+        "d2h_compact_ms_per_step_slowest_rank": d2h_compact / d2h_min / 1e6, "device_ms_per_step": ms / args.steps,
+        "note": "copy rates with every rank copying at once; the downloads overlap the adaptor and the CTC head (a few ms of the step), "
+                "so whatever of d2h_ms exceeds that window is exposed",
+    }
 
     # ---- roofline: one extra step with per-launch CUDA events
     prof = None
@@ -510,7 +540,9 @@ def run_ours(args) -> None:
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": args.steps,
                 "api": "fa_front_half (host buffers, pinned; enc_output + adaptor_output + ids come back in full, ORT-shaped)",
                 "compact": {"value": e2e_compact_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_compact,
-                            "api": "fa_front_half_embd (enc_output + ids in full; of adaptor_output only rows [0, target_len) of each segment)"}},
+                            "api": "fa_front_half_embd (ids in full; of adaptor_output only rows [0, target_len) of each segment — what the "
+                                   "LLM reads; enc_output stays on the device, its only consumer, the CTC head, has already run)"},
+                "copy_breakdown": copy_breakdown},
         "gpu_launches": launches,
         "roofline": roofline,
     }

@@ -280,15 +280,22 @@ __device__ __forceinline__ void epilogue_unit(const EpiParams& ep, const CUtenso
             FA_GT(g1 = clock64(); gt[6] += g1 - g0; g0 = g1;)    // fp32 store: smem write, fence, issue
         }
         if (ep.out_f8) {
-            // e4m3 (round to nearest even, saturating at +-448): a thread owns 32 consecutive bytes of its row, one sector
-            if (row < m && col0 + 32 <= n) {
-                uint32_t w8[8];
+            // e4m3 (round to nearest even, saturating at +-448): a thread owns 32 consecutive bytes of its row; the 1 KB
+            // tile leaves as a tensor store like the other output forms (map_pl is the e4m3 map in this case; rows and
+            // columns past the matrix edge are clipped by it)
+            uint32_t w8[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) w8[j] = f32x4_to_e4m3(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                uint4* dst = reinterpret_cast<uint4*>(ep.out_f8 + (int64_t)row * ep.ld8 + col0);
-                dst[0] = make_uint4(w8[0], w8[1], w8[2], w8[3]);
-                dst[1] = make_uint4(w8[4], w8[5], w8[6], w8[7]);
+            for (int j = 0; j < 8; ++j) w8[j] = f32x4_to_e4m3(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            stg_acquire();
+            *reinterpret_cast<uint4*>(stg + lane * 32) = make_uint4(w8[0], w8[1], w8[2], w8[3]);
+            *reinterpret_cast<uint4*>(stg + lane * 32 + 16) = make_uint4(w8[4], w8[5], w8[6], w8[7]);
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_2d(map_pl, stg_s, col0, row_base);
+                bulk_commit();
             }
+            store_pending = true;
         }
         if (ep.out_hi) {
             if (col0 < ep.pl_col_scale_end) {                    // warp-uniform: the q columns of a fused q|k|v projection
@@ -1145,6 +1152,12 @@ void launch_gemm_tc(const TcOperand& a, const TcOperand& w, int m, int n, int k,
     // A gated launch whose gate is closed executes nothing: it is booked at 0 FLOP under its own key (the gate is
     // only known on the device; the second-chance vocabulary pass is the one gated launch and its gate is closed
     // unless a candidate list overflowed).
+    if (ep.out_f8) {
+        FA_REQUIRE(!ep.out_hi, "a launch writes bf16 planes or e4m3, not both");
+        const cuuint64_t dims[2] = {(cuuint64_t)n, (cuuint64_t)m};
+        const cuuint64_t strides[1] = {(cuuint64_t)e.ld8};
+        map_pl = make_store_map(CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, ep.out_f8, 2, dims, strides, CU_TENSOR_MAP_SWIZZLE_NONE);
+    }
     prof_note_work(e.gate ? 0.0 : 2.0 * m * (double)n * k, 0.0);
     if (g_prof_on) {
         char tag[64];
