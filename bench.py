@@ -45,11 +45,14 @@ BATCH = 32
 METRIC = "encoder+adaptor+CTC throughput (fbank -> SAN-M encoder -> adaptor -> CTC greedy ids), batched 60 s segments"
 UNIT = "audio-s/s"
 WORKLOADS = {
+    "config1": "configs[0]: ONE 60 s segment per call (the reference's own call pattern), fbank+encoder+adaptor+CTC greedy; a latency line: "
+               "ms_per_step is the device time of a call, e2e.ms_per_call the host-buffer call (CUDA-graph replay)",
     "config2": "configs[1]: batch 32 x 60 s synthetic segments, fbank+encoder+adaptor+CTC greedy on 1 B200 (per GPU)",
     "config3": "configs[2]: mixed-length batch, 32 segments of randint(80 000, 960 001) samples (seed 1234 + rank) zero-padded "
                "to the batch maximum with per-segment ilens, per GPU; value counts VALID audio seconds",
     "config4": "configs[3]: 1 h of synthetic audio cut 60 s / 4 s overlap (65 windows: 64 x 60 s + 1 x 16 s), windows dealt "
-               "round-robin over the GPUs (strong scaling); value counts the file's 3600 s",
+               "round-robin over the GPUs (strong scaling) and run as ragged batches (every window at its own physical length); "
+               "value counts the file's 3600 s",
     "config5": "configs[4]: 256 x 60 s segments split over the GPUs in batches of 32 (strong scaling)",
 }
 
@@ -211,9 +214,13 @@ def make_plan(args, world: int, rank: int) -> "list[Plan]":
     s60 = SEG_S * SR
     plans = []
     for alt in range(2):
-        if args.workload == "config2":
+        if args.workload == "config1":
+            batches = [(white_batch(1, rank * 1000 + alt).pin_memory(), [s60], None)]
+            plans.append(Plan(batches, world * SEG_S, "weak", 1, s60,
+                              {"l2": "a call streams the 2.2 GB of weight planes (>> 126 MB L2); the 3.8 MB input alternates between two buffers"}))
+        elif args.workload == "config2":
             b = args.batch
-            batches = [(white_batch(b, rank * 1000 + alt * b).pin_memory(), [s60] * b)]
+            batches = [(white_batch(b, rank * 1000 + alt * b).pin_memory(), [s60] * b, None)]
             plans.append(Plan(batches, world * b * SEG_S, "weak", b, s60, None))
         elif args.workload == "config3":
             g = torch.Generator().manual_seed(1234 + rank + 100 * alt)
@@ -223,7 +230,7 @@ def make_plan(args, world: int, rank: int) -> "list[Plan]":
             for i, n in enumerate(lens):
                 rows[i, :n] = synth.white(n, rank * 1000 + alt * args.batch + i)
             # every rank draws from the same distribution: the job's valid seconds are summed over ranks by the caller
-            plans.append(Plan([(rows.pin_memory(), lens)], sum(lens) / SR, "weak", args.batch, 960_000,
+            plans.append(Plan([(rows.pin_memory(), lens, None)], sum(lens) / SR, "weak", args.batch, 960_000,
                               {"valid_s_this_rank": sum(lens) / SR, "physical_s_this_rank": args.batch * s_phys / SR}))
         elif args.workload == "config4":
             n = 3600 * SR
@@ -231,22 +238,25 @@ def make_plan(args, world: int, rank: int) -> "list[Plan]":
             mine = Sg.shard(len(windows), world, rank)
             # the file: 60 one-minute white segments; each window is cut out of it exactly as the orchestrator would
             base = torch.cat([synth.white(s60, 5000 + alt * 100 + i) for i in range(60)])
-            by_len = {}
-            for i in mine:
-                by_len.setdefault(windows[i][1] - windows[i][0], []).append(i)
+            # all of a rank's windows — the 16 s tail included — in evenly sized RAGGED batches: every window keeps its own
+            # physical length (fa_front_half_ragged), as lookahead.run_file batches a file
+            order = sorted(mine, key=lambda i: windows[i][0] - windows[i][1])
+            n_b = -(-len(order) // args.batch)
             batches = []
-            for ln, idx in sorted(by_len.items(), reverse=True):
-                for b0 in range(0, len(idx), args.batch):
-                    grp = idx[b0:b0 + args.batch]
-                    rows = torch.stack([base[windows[i][0]:windows[i][1]] for i in grp]).contiguous()
-                    batches.append((rows.pin_memory(), [ln] * len(grp)))
+            for k in range(n_b):
+                grp = order[k::n_b]
+                lens = [windows[i][1] - windows[i][0] for i in grp]
+                rows = torch.zeros((len(grp), max(lens)), dtype=torch.float32)
+                for r, i in enumerate(grp):
+                    rows[r, :lens[r]] = base[windows[i][0]:windows[i][1]]
+                batches.append((rows.pin_memory(), lens, lens if min(lens) < max(lens) else None))
             plans.append(Plan(batches, 3600.0, "strong", args.batch, s60, {"windows": len(windows), "windows_this_rank": len(mine)}))
         elif args.workload == "config5":
             per = 256 // world
             batches = []
             for b0 in range(0, per, args.batch):
                 nb = min(args.batch, per - b0)
-                batches.append((white_batch(nb, 7000 + alt * 512 + rank * per + b0).pin_memory(), [s60] * nb))
+                batches.append((white_batch(nb, 7000 + alt * 512 + rank * per + b0).pin_memory(), [s60] * nb, None))
             plans.append(Plan(batches, 256.0 * SEG_S, "strong", args.batch, s60, {"segments_this_rank": per}))
         else:
             raise SystemExit(f"unknown workload {args.workload}")
@@ -287,17 +297,18 @@ def run_ours(args) -> None:
     eng.use_torch_stream()
 
     # device-resident inputs and outputs for `value`
-    dev_in = [[(h.to(dev, non_blocking=True), lens) for h, lens in p.batches] for p in plans]
-    bmax = max(h.shape[0] for p in plans for h, _ in p.batches)
-    tmax = eng.frames(max(h.shape[1] for p in plans for h, _ in p.batches))
+    dev_in = [[(h.to(dev, non_blocking=True), lens, phys) for h, lens, phys in p.batches] for p in plans]
+    bmax = max(h.shape[0] for p in plans for h, _, _ in p.batches)
+    tmax = eng.frames(max(h.shape[1] for p in plans for h, _, _ in p.batches))
     enc = torch.empty((bmax * tmax * 512,), dtype=torch.float32, device=dev)
     ad = torch.empty((bmax * tmax * 1024,), dtype=torch.float32, device=dev)
     ids = torch.empty((bmax * tmax,), dtype=torch.int32, device=dev)
 
     def step(i):
-        for a, lens in dev_in[i & 1]:
+        for a, lens, phys in dev_in[i & 1]:
             b, t = a.shape[0], eng.frames(a.shape[1])
-            eng.front_half_cuda(a, lens, enc[: b * t * 512].view(b, t, 512), ad[: b * t * 1024].view(b, t, 1024), ids[: b * t].view(b, t))
+            eng.front_half_cuda(a, lens, enc[: b * t * 512].view(b, t, 512), ad[: b * t * 1024].view(b, t, 1024), ids[: b * t].view(b, t),
+                                phys=phys)
 
     def fence():
         torch.cuda.synchronize()
@@ -350,10 +361,13 @@ def run_ours(args) -> None:
     h_embd = torch.empty((bmax * 128, 1024), dtype=torch.float32).pin_memory()
 
     def e2e_step(i, compact=False):
-        for h, lens in plans[i & 1].batches:
+        for h, lens, phys in plans[i & 1].batches:
             b, s = h.shape
             arr = (C.c_int64 * b)(*lens)
-            if not compact:
+            if phys is not None:           # ragged batch: the full-array form only
+                _lib.check(eng.lib.fa_front_half_ragged(eng._h, C.c_void_p(h.data_ptr()), b, s, arr, (C.c_int64 * b)(*phys),
+                                                        C.c_void_p(h_enc.data_ptr()), C.c_void_p(h_ad.data_ptr()), C.c_void_p(h_ids.data_ptr())))
+            elif not compact:
                 _lib.check(eng.lib.fa_front_half(eng._h, C.c_void_p(h.data_ptr()), b, s, arr, C.c_void_p(h_enc.data_ptr()),
                                                  C.c_void_p(h_ad.data_ptr()), C.c_void_p(h_ids.data_ptr())))
             else:
@@ -380,9 +394,9 @@ def run_ours(args) -> None:
     e2e_s = time_e2e(False)
     e2e_compact_s = time_e2e(True)
     e2e_value, e2e_compact_value = audio_s_total / e2e_s, audio_s_total / e2e_compact_s
-    h2d = sum(h.numel() * 4 for h, _ in P0.batches)
-    d2h = sum(h.shape[0] * eng.frames(h.shape[1]) * (512 + 1024 + 1) * 4 for h, _ in P0.batches)
-    d2h_compact = sum(h.shape[0] * eng.frames(h.shape[1]) * 4 + sum(eng.target_len(n) for n in lens) * 4096 for h, lens in P0.batches)
+    h2d = sum(h.numel() * 4 for h, _, _ in P0.batches)
+    d2h = sum(h.shape[0] * eng.frames(h.shape[1]) * (512 + 1024 + 1) * 4 for h, _, _ in P0.batches)
+    d2h_compact = sum(h.shape[0] * eng.frames(h.shape[1]) * 4 + sum(eng.target_len(n) for n in lens) * 4096 for h, lens, _ in P0.batches)
 
     # ---- what the host link gives each rank while ALL ranks copy at once (the e2e limiter at N = 8): the step's own
     # buffers, host -> device and device -> host, timed alone with CUDA events
@@ -500,7 +514,7 @@ def run_ours(args) -> None:
     # ---- cpu baseline (bounded sample) and the parity of one step's output against it
     cpu, parity = None, None
     if world == 1 and not args.no_cpu_baseline:
-        h, lens = P0.batches[0]
+        h, lens, _ = P0.batches[0]
         n_rows = min(args.cpu_rows, h.shape[0])
         b, s = h.shape
         t = eng.frames(s)
@@ -532,12 +546,13 @@ def run_ours(args) -> None:
                          "projection bf16, fp32 accumulate, fp32 LayerNorm/softmax; SPEED MODE with an id-mismatch budget, not token-exact)",
                   "fp32": "f32"}[args.precision],
         "data": "synthetic (0.1*N(0,1) clipped, seed 1234+i); random-init weights of the architecture (no checkpoint ships)",
-        "config": {"workload": WORKLOADS[args.workload], "segments_per_step_this_rank": sum(h.shape[0] for h, _ in P0.batches),
+        "config": {"workload": WORKLOADS[args.workload], "segments_per_step_this_rank": sum(h.shape[0] for h, _, _ in P0.batches),
                    "batches_per_step_this_rank": len(P0.batches), "segment_s": SEG_S, "audio_s_per_step_all_ranks": audio_s_total / args.steps,
                    "precision": args.precision, "parallelism": f"segment-dp{world}", "numa_bind": numa, "detail": P0.note,
                    "l2": "inputs alternate between two sets of >= 123 MB and a step streams GBs of activations, both > 126 MB L2"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": args.steps,
+                "ms_per_call": e2e_s / args.steps * 1e3 / max(len(P0.batches), 1),
                 "api": "fa_front_half (host buffers, pinned; enc_output + adaptor_output + ids come back in full, ORT-shaped)",
                 "compact": {"value": e2e_compact_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_compact,
                             "api": "fa_front_half_embd (ids in full; of adaptor_output only rows [0, target_len) of each segment — what the "

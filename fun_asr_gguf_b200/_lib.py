@@ -37,6 +37,9 @@ SIGNATURES = {
     "fa_ctc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "fa_ctc_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "fa_front_half": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, c_i64_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fa_front_half_ragged": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, c_i64_p, c_i64_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fa_front_half_ragged_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, c_i64_p, c_i64_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p]),
     "fa_front_half_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, c_i64_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fa_front_half_embd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, c_i64_p, C.c_void_p, C.POINTER(C.c_void_p), c_i64_p,
                            C.c_void_p]),

@@ -121,6 +121,22 @@ int fa_front_half(fa_ctx* ctx, const float* audio, int batch, int64_t samples, c
     });
 }
 
+int fa_front_half_ragged(fa_ctx* ctx, const float* audio, int batch, int64_t samples, const int64_t* ilens, const int64_t* phys,
+                         float* enc, float* adaptor, int32_t* ids) {
+    return guarded([&] {
+        NEED(ctx); NEED(audio); NEED(ilens); NEED(phys); NEED(ids);
+        ctx->impl.front_half_host(audio, batch, samples, ilens, enc, adaptor, ids, nullptr, nullptr, phys);
+    });
+}
+
+int fa_front_half_ragged_dev(fa_ctx* ctx, const float* audio, int batch, int64_t samples, const int64_t* ilens, const int64_t* phys,
+                             float* enc, float* adaptor, int32_t* ids) {
+    return guarded([&] {
+        NEED(ctx); NEED(audio); NEED(ilens); NEED(phys); NEED(ids);
+        ctx->impl.front_half_dev(audio, batch, samples, ilens, enc, adaptor, ids, phys);
+    });
+}
+
 int fa_front_half_dev(fa_ctx* ctx, const float* audio, int batch, int64_t samples, const int64_t* ilens, float* enc,
                       float* adaptor, int32_t* ids) {
     return guarded([&] {

@@ -382,7 +382,7 @@ void Context::finalize() {
         logits_.alloc((size_t)logits_rows_ * vocab_ * 4);
     }
     // n_valid, t_valid, target_len, seg_off[B+1], order[B], tile_off[B+1]; CTC head: seg_off[B+1], tile_off[B+1], len[B], bias[B]
-    len_ints_ = 10 * max_batch_ + 4;
+    len_ints_ = 11 * max_batch_ + 4;             // + t_phys[B] (ragged batches)
     lens_.alloc((size_t)len_ints_ * sizeof(int));
     d_nvalid_ = lens_.as<int>();
     d_tvalid_ = d_nvalid_ + max_batch_;
@@ -571,7 +571,7 @@ void Context::projector(const Projector& P, const Act& in, int batch, int frames
 
 // ------------------------------------------------------------------------------------ graphs
 
-void Context::stage_lengths(int batch, int64_t s_phys, const int64_t* h_ilens, bool allow_packed) {
+void Context::stage_lengths(int batch, int64_t s_phys, const int64_t* h_ilens, bool allow_packed, const int64_t* h_phys) {
     const int slot = len_next_;
     len_next_ = (len_next_ + 1) % kLenSlots;
     FA_CUDA(cudaEventSynchronize(len_ev_[slot]));
@@ -584,12 +584,15 @@ void Context::stage_lengths(int batch, int64_t s_phys, const int64_t* h_ilens, b
     int* h_tile_c = h_off_c + max_batch_ + 1;    // [B+1]
     int* h_len_c = h_tile_c + max_batch_ + 1;    // [B]
     float* h_bias_c = reinterpret_cast<float*>(h_len_c + max_batch_);     // [B]
+    int* h_tphys = h_len_c + 2 * max_batch_;     // [B]
     const int frames = lfr_frames_of(s_phys);
     int total = 0, longest = 0;
     double sq = 0.0;
     for (int b = 0; b < batch; ++b) {
         const int64_t nv = h_ilens[b];
         FA_REQUIRE(nv >= 1 && nv <= s_phys, "ilens must satisfy 1 <= ilens[b] <= samples");
+        FA_REQUIRE(!h_phys || (h_phys[b] >= nv && h_phys[b] <= s_phys), "phys must satisfy ilens[b] <= phys[b] <= samples");
+        h_tphys[b] = h_phys ? lfr_frames_of(h_phys[b]) : frames;
         hl[b] = (int)nv;
         h_tv[b] = lfr_frames_of(nv);
         hl[2 * max_batch_ + b] = target_len_of(nv);
@@ -602,6 +605,13 @@ void Context::stage_lengths(int batch, int64_t s_phys, const int64_t* h_ilens, b
     h_off[batch] = total;
     // Packed execution only pays (and only differs) when the batch holds padded frames
     packed_ = allow_packed && allow_packed_env_ && prec_ != kFp32 && !simt_attention_ && !taps_on_ && total < batch * frames;
+    if (h_phys) {
+        // a ragged batch only exists in the packed layout (every segment keeps its own physical length)
+        FA_REQUIRE(allow_packed && prec_ != kFp32 && !simt_attention_ && !taps_on_,
+                   "per-segment physical lengths need the padding-free path (a tensor-core precision mode, no debug taps)");
+        packed_ = true;
+    }
+    d_tphys_ = nullptr;
     if (packed_) {
         // attention items are dealt round-robin over the CTAs: longest segments first, so that every CTA's share
         // mixes long and short items (the cost of an item is proportional to its segment's length)
@@ -617,7 +627,7 @@ void Context::stage_lengths(int batch, int64_t s_phys, const int64_t* h_ilens, b
         int total_c = 0, tiles_c = 0;
         double sq_c = 0.0;
         for (int b = 0; b < batch; ++b) {
-            const int n_pad = frames - h_tv[b];
+            const int n_pad = h_tphys[b] - h_tv[b];        // zero-padded frames of the segment at ITS physical length
             h_len_c[b] = h_tv[b] + (n_pad > 0 ? 1 : 0);
             h_bias_c[b] = n_pad > 1 ? std::log2((float)n_pad) : 0.f;
             h_off_c[b] = total_c;
@@ -633,6 +643,7 @@ void Context::stage_lengths(int batch, int64_t s_phys, const int64_t* h_ilens, b
         pk_ctc_.tile_off = pk_ctc_.seg_off + max_batch_ + 1;
         d_len_ctc_ = pk_ctc_.tile_off + max_batch_ + 1;
         pk_ctc_.last_key_bias = reinterpret_cast<const float*>(d_len_ctc_ + max_batch_);
+        if (h_phys) d_tphys_ = d_len_ctc_ + 2 * max_batch_;
         pk_ctc_.total_rows = total_c; pk_ctc_.total_tiles = tiles_c; pk_ctc_.max_len = longest + 1; pk_ctc_.sum_len_sq = sq_c;
     }
     ctc_packed_ready_ = false;
@@ -809,16 +820,16 @@ void Context::ctc_graph(const Act& in, int batch, int frames, int32_t* d_ids, co
         vocab_argmax(x, h_act(kDenc).pl, ctc_lo_, vocab_wnorm_, M, vocab_rescore_ ? cand_workspace() : VocabCand{},
                      amax_val_.as<float>(), amax_idx_.as<int32_t>(), ids_rows);
     }
-    if (pk) launch_unpack_ids(ids_rows, d_ids, batch, frames, pk->seg_off, d_tvalid_, stream_);
+    if (pk) launch_unpack_ids(ids_rows, d_ids, batch, frames, pk->seg_off, d_tvalid_, stream_, d_tphys_);
 }
 
 void Context::front_half_dev(const float* d_audio, int batch, int64_t s_phys, const int64_t* h_ilens, float* d_enc,
-                             float* d_adaptor, int32_t* d_ids) {
+                             float* d_adaptor, int32_t* d_ids, const int64_t* h_phys) {
     ensure_room(batch, s_phys);
     set_device();
     if (!d_enc) d_enc = enc_.as<float>();
     if (!d_adaptor) d_adaptor = adaptor_out_.as<float>();
-    stage_lengths(batch, s_phys, h_ilens, true);
+    stage_lengths(batch, s_phys, h_ilens, true, h_phys);
     front_end(d_audio, 0, batch, s_phys);
     fused_ctc_next_ = true;
     try { encoder_graph(batch, s_phys, d_enc, d_adaptor); } catch (...) { fused_ctc_next_ = false; throw; }
@@ -923,7 +934,8 @@ void Context::ctc_host(const float* enc, int batch, int frames, int32_t* ids) {
 
 // ids == nullptr: encoder session only
 void Context::front_half_host(const float* audio, int batch, int64_t s_phys, const int64_t* ilens, float* enc,
-                              float* adaptor, int32_t* ids, float* const* embd_rows, int64_t* rows_out) {
+                              float* adaptor, int32_t* ids, float* const* embd_rows, int64_t* rows_out, const int64_t* phys) {
+    FA_REQUIRE(!phys || ids, "a ragged batch runs both graphs in one call");
     ensure_room(1, s_phys);
     set_device();
     const int frames = lfr_frames_of(s_phys);
@@ -940,8 +952,8 @@ void Context::front_half_host(const float* audio, int batch, int64_t s_phys, con
     };
     for (int b0 = 0; b0 < batch; b0 += max_batch_) {
         const int nb = std::min(max_batch_, batch - b0);
-        stage_lengths(nb, s_phys, ilens + b0, !use_graph(nb));
-        if (use_graph(nb)) {
+        stage_lengths(nb, s_phys, ilens + b0, phys || !use_graph(nb), phys ? phys + b0 : nullptr);
+        if (!phys && use_graph(nb)) {
             // launch-bound regime: one upload, one graph (front end, encoder, adaptor and, if asked for, the CTC head),
             // downloads behind it on the same stream
             FA_CUDA(cudaMemcpyAsync(audio_.p, audio + (size_t)b0 * s_phys, (size_t)nb * s_phys * 4, cudaMemcpyHostToDevice, stream_));

@@ -78,7 +78,7 @@ public:
     void ctc_dev(const float* d_enc, int batch, int frames, int32_t* d_ids);
     // both graphs back to back on device pointers (d_enc / d_adaptor may be null: the context's own buffers are used)
     void front_half_dev(const float* d_audio, int batch, int64_t s_phys, const int64_t* h_ilens, float* d_enc, float* d_adaptor,
-                        int32_t* d_ids);
+                        int32_t* d_ids, const int64_t* h_phys = nullptr);
     void collapse_dev(const int32_t* d_ids, int batch, int frames, int32_t* d_tokens, int32_t* d_starts,
                       int32_t* d_counts);
     // host-pointer executions (copies inside); synchronous
@@ -86,8 +86,11 @@ public:
     void ctc_host(const float* enc, int batch, int frames, int32_t* ids);
     // embd_rows != nullptr: segment b's adaptor rows [0, target_len) go to embd_rows[b] (host or device memory) and
     // rows_out[b] = target_len; `adaptor` is then ignored
+    // phys != nullptr (ragged batch): segment b is computed as the reference computes it at ITS OWN physical length phys[b]
+    // (ilens[b] <= phys[b] <= s_phys, s_phys being the row stride of `audio`); needs a tensor-core precision mode
     void front_half_host(const float* audio, int batch, int64_t s_phys, const int64_t* ilens, float* enc,
-                         float* adaptor, int32_t* ids, float* const* embd_rows = nullptr, int64_t* rows_out = nullptr);
+                         float* adaptor, int32_t* ids, float* const* embd_rows = nullptr, int64_t* rows_out = nullptr,
+                         const int64_t* phys = nullptr);
 
     void sync() { set_device(); FA_CUDA(cudaStreamSynchronize(stream_)); }
     void set_stream(cudaStream_t s);
@@ -129,7 +132,7 @@ private:
     void tap(const char* name, const float* d, int64_t rows, int64_t cols);
     void ensure_room(int batch, int64_t s_phys) const;
     // encode_dev in three parts, so that the host variants can overlap copies with the front end
-    void stage_lengths(int batch, int64_t s_phys, const int64_t* h_ilens, bool allow_packed);
+    void stage_lengths(int batch, int64_t s_phys, const int64_t* h_ilens, bool allow_packed, const int64_t* h_phys = nullptr);
     void front_end(const float* d_audio, int b0, int nb, int64_t s_phys);
     void encoder_graph(int batch, int64_t s_phys, float* d_enc, float* d_adaptor, bool record_events = true);
     // Small batches are launch-bound (some 620 launches per 60 s segment against a few milliseconds of GPU work):
@@ -185,6 +188,7 @@ private:
     Packing pk_;                 // encoder + adaptor rows
     Packing pk_ctc_;             // CTC head rows: the valid frames of a segment plus ONE row for all its padded frames
     const int* d_len_ctc_ = nullptr;          // [batch] rows of each segment in the head's packing
+    const int* d_tphys_ = nullptr;            // [batch] LFR frames of each segment's own physical length (ragged batches), else null
     bool fused_ctc_next_ = false;             // the CTC head follows in this call: encoder_graph prepares its packed input
     Act ctc_packed_input() const;
     bool ctc_packed_ready_ = false;           // encoder_graph left the head's packed input in encpl_ / enc8_

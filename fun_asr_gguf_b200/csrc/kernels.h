@@ -80,7 +80,9 @@ void launch_row_keep(const float* in, float* out, int batch, int frames, int d, 
 void launch_repack_rows(const void* src, void* dst, int row_bytes, const int* src_off, const int* dst_off, const int* tv,
                         int batch, int max_len, cudaStream_t st);
 // ids of the head's packed rows -> physical [batch][frames]: frame t >= tv[b] takes the id of the segment's pad row
-void launch_unpack_ids(const int32_t* packed, int32_t* ids, int batch, int frames, const int* off, const int* tv, cudaStream_t st);
+// tphys != nullptr (ragged batches): frames t >= tphys[b] get -1
+void launch_unpack_ids(const int32_t* packed, int32_t* ids, int batch, int frames, const int* off, const int* tv, cudaStream_t st,
+                       const int* tphys = nullptr);
 // fp32 -> planes
 void launch_split_planes(const float* x, int64_t n, Planes out, cudaStream_t st);
 // fp32 -> e4m3 (round to nearest even, saturating)

@@ -281,12 +281,13 @@ k_repack_rows(const uint4* __restrict__ src, uint4* __restrict__ dst, int row16,
 
 __global__ void __launch_bounds__(256)
 k_unpack_ids(const int32_t* __restrict__ packed, int32_t* __restrict__ ids, int frames, const int* __restrict__ off,
-             const int* __restrict__ tv) {
+             const int* __restrict__ tv, const int* __restrict__ tphys) {
     grid_dependency_wait();
     const int b = blockIdx.y, t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= frames) return;
     const int n = tv[b];
-    ids[(int64_t)b * frames + t] = packed[off[b] + (t < n ? t : n)];
+    // frames past a segment's own physical length (ragged batches) do not exist in the reference's run of it: -1
+    ids[(int64_t)b * frames + t] = (tphys && t >= tphys[b]) ? -1 : packed[off[b] + (t < n ? t : n)];
 }
 
 __global__ void __launch_bounds__(256)
@@ -623,8 +624,9 @@ void launch_repack_rows(const void* src, void* dst, int row_bytes, const int* sr
               row_bytes / 16, src_off, dst_off, tv);
 }
 
-void launch_unpack_ids(const int32_t* packed, int32_t* ids, int batch, int frames, const int* off, const int* tv, cudaStream_t st) {
-    FA_LAUNCH(k_unpack_ids, dim3(cdiv(frames, 256), batch), 256, 0, st, packed, ids, frames, off, tv);
+void launch_unpack_ids(const int32_t* packed, int32_t* ids, int batch, int frames, const int* off, const int* tv, cudaStream_t st,
+                       const int* tphys) {
+    FA_LAUNCH(k_unpack_ids, dim3(cdiv(frames, 256), batch), 256, 0, st, packed, ids, frames, off, tv, tphys);
 }
 
 void launch_split_planes(const float* x, int64_t n, Planes out, cudaStream_t st) {

@@ -58,6 +58,11 @@ class FrontHalf:
         except Exception:
             pass
 
+    @property
+    def supports_ragged(self) -> bool:
+        """Per-segment physical lengths (front_half(..., phys=...)) need the padding-free path: a tensor-core mode."""
+        return self.precision != "fp32"
+
     # ------------------------------------------------------------------ shapes
     @staticmethod
     def frames(samples: int) -> int:
@@ -96,16 +101,25 @@ class FrontHalf:
         _lib.check(self.lib.fa_ctc(self._h, _ptr(enc), b, t, _ptr(ids)))
         return ids
 
-    def front_half(self, audio: np.ndarray, ilens: Sequence[int], want_enc: bool = True, want_adaptor: bool = True):
-        """Both graphs back to back; enc never leaves the device between them."""
+    def front_half(self, audio: np.ndarray, ilens: Sequence[int], want_enc: bool = True, want_adaptor: bool = True,
+                   phys: Optional[Sequence[int]] = None):
+        """Both graphs back to back; enc never leaves the device between them.
+
+        phys (fa_front_half_ragged): per-segment PHYSICAL sample counts, ilens[b] <= phys[b] <= audio.shape[1].  Segment b
+        is then computed as the reference computes it when fed at physical length phys[b], whatever else is in the batch;
+        ids[b, frames(phys[b]):] are -1."""
         audio = np.ascontiguousarray(audio, dtype=np.float32)
         b, s = audio.shape
         t = self.frames(s)
         enc = np.empty((b, t, W.D_ENC), np.float32) if want_enc else None
         ad = np.empty((b, t, W.D_LLM), np.float32) if want_adaptor else None
         ids = np.empty((b, t), np.int32)
-        _lib.check(self.lib.fa_front_half(self._h, _ptr(audio), b, s, self._ilens(ilens, b),
-                                          _ptr(enc) if want_enc else None, _ptr(ad) if want_adaptor else None, _ptr(ids)))
+        if phys is None:
+            _lib.check(self.lib.fa_front_half(self._h, _ptr(audio), b, s, self._ilens(ilens, b),
+                                              _ptr(enc) if want_enc else None, _ptr(ad) if want_adaptor else None, _ptr(ids)))
+        else:
+            _lib.check(self.lib.fa_front_half_ragged(self._h, _ptr(audio), b, s, self._ilens(ilens, b), self._ilens(phys, b),
+                                                     _ptr(enc) if want_enc else None, _ptr(ad) if want_adaptor else None, _ptr(ids)))
         return enc, ad, ids
 
     def front_half_into(self, audio: np.ndarray, ilens: Sequence[int], embd: np.ndarray, row_offset: int = 0,
@@ -176,7 +190,7 @@ class FrontHalf:
         _lib.check(self.lib.fa_ctc_dev(self._h, C.c_void_p(enc.data_ptr()), b, t, C.c_void_p(ids.data_ptr())))
         return ids
 
-    def front_half_cuda(self, audio, ilens: Sequence[int], enc=None, adaptor=None, ids=None):
+    def front_half_cuda(self, audio, ilens: Sequence[int], enc=None, adaptor=None, ids=None, phys: Optional[Sequence[int]] = None):
         """Both graphs back to back on CUDA tensors (fa_front_half_dev); asynchronous on the context's stream.  Mixed-length
         batches stay padding-free through the CTC head as well.  Returns (enc, adaptor, ids)."""
         import torch
@@ -189,8 +203,13 @@ class FrontHalf:
             adaptor = torch.empty((b, t, W.D_LLM), dtype=torch.float32, device=audio.device)
         if ids is None:
             ids = torch.empty((b, t), dtype=torch.int32, device=audio.device)
-        _lib.check(self.lib.fa_front_half_dev(self._h, C.c_void_p(audio.data_ptr()), b, s, self._ilens(ilens, b),
-                                              C.c_void_p(enc.data_ptr()), C.c_void_p(adaptor.data_ptr()), C.c_void_p(ids.data_ptr())))
+        if phys is None:
+            _lib.check(self.lib.fa_front_half_dev(self._h, C.c_void_p(audio.data_ptr()), b, s, self._ilens(ilens, b),
+                                                  C.c_void_p(enc.data_ptr()), C.c_void_p(adaptor.data_ptr()), C.c_void_p(ids.data_ptr())))
+        else:
+            _lib.check(self.lib.fa_front_half_ragged_dev(self._h, C.c_void_p(audio.data_ptr()), b, s, self._ilens(ilens, b),
+                                                         self._ilens(phys, b), C.c_void_p(enc.data_ptr()),
+                                                         C.c_void_p(adaptor.data_ptr()), C.c_void_p(ids.data_ptr())))
         return enc, adaptor, ids
 
     def collapse_cuda(self, ids):

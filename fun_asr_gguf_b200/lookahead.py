@@ -12,9 +12,11 @@ decoding.  Nothing in those calls depends on the previous window, so all of them
     # the unchanged per-segment encoder / CTC session calls now return the precomputed arrays
 
 Physical lengths are the ones `encode_audio` would feed (the native window length, or 1 s for a shorter
-one — the CPU-provider rule at nano_onnx.py:90-99), and only windows of EQUAL physical length share a batch:
-the unmasked CTC head's ids depend on the physical length, so padding a short window up to a
-longer one would change them.  Results are therefore identical to the per-segment calls.
+one — the CPU-provider rule at nano_onnx.py:90-99).  The unmasked CTC head's ids depend on the physical length
+(SURVEY F7), so padding a short window up to a longer one would change them; the engine's ragged call
+(`fa_front_half_ragged`) lets every window keep its own physical length inside a shared batch, so ALL windows of a
+file — the short tail included — go through together (an engine without it, the fp32 arbiter mode, falls back to
+batches of equal physical length).  Results are therefore identical to the per-segment calls.
 """
 from __future__ import annotations
 
@@ -102,9 +104,37 @@ def run_file(engine, audio: np.ndarray, segment_s: float = 60.0, overlap_s: floa
     windows = S.segment_windows(audio.shape[0], segment_s, overlap_s)
     mine = S.shard(len(windows), world, rank)
     out: List[Optional[SegmentFront]] = [None] * len(windows)
+    def emit(group, batch, lens, n_phys, enc, ad, ids):
+        for r, i in enumerate(group):
+            t = W.lfr_frames(n_phys[r])
+            seg = SegmentFront(window=windows[i], n_valid=lens[r], n_phys=n_phys[r],
+                               enc_output=np.ascontiguousarray(enc[r:r + 1, :t]), adaptor_output=np.ascontiguousarray(ad[r:r + 1, :t]),
+                               ids=np.ascontiguousarray(ids[r:r + 1, :t]), target_len=W.adaptor_target_len(lens[r]))
+            out[i] = seg
+            if cache is not None:
+                cache.put(batch[r, :n_phys[r]], seg)
+
+    phys_of = {i: physical_samples(windows[i][1] - windows[i][0]) for i in mine}
+    if getattr(engine, "supports_ragged", False):
+        # every window keeps ITS OWN physical length inside a shared batch (fa_front_half_ragged), so windows of any
+        # lengths — the short tail of a file included — go through together, in evenly sized batches
+        order = sorted(mine, key=lambda i: -phys_of[i])
+        n_batches = -(-len(order) // engine.max_batch) if order else 0
+        for k in range(n_batches):
+            group = order[k::n_batches]
+            n_phys = [phys_of[i] for i in group]
+            batch = np.zeros((len(group), max(n_phys)), np.float32)
+            lens = []
+            for r, i in enumerate(group):
+                a, b = windows[i]
+                batch[r, :b - a] = audio[a:b]
+                lens.append(b - a)
+            enc, ad, ids = engine.front_half(batch, lens, phys=n_phys)
+            emit(group, batch, lens, n_phys, enc, ad, ids)
+        return out
     by_phys: Dict[int, List[int]] = {}
     for i in mine:
-        by_phys.setdefault(physical_samples(windows[i][1] - windows[i][0]), []).append(i)
+        by_phys.setdefault(phys_of[i], []).append(i)
     for n_phys, idx in sorted(by_phys.items(), reverse=True):
         for b0 in range(0, len(idx), engine.max_batch):
             group = idx[b0:b0 + engine.max_batch]
@@ -115,13 +145,7 @@ def run_file(engine, audio: np.ndarray, segment_s: float = 60.0, overlap_s: floa
                 batch[r, :b - a] = audio[a:b]
                 lens.append(b - a)
             enc, ad, ids = engine.front_half(batch, lens)
-            for r, i in enumerate(group):
-                seg = SegmentFront(window=windows[i], n_valid=lens[r], n_phys=n_phys,
-                                   enc_output=np.ascontiguousarray(enc[r:r + 1]), adaptor_output=np.ascontiguousarray(ad[r:r + 1]),
-                                   ids=np.ascontiguousarray(ids[r:r + 1]), target_len=W.adaptor_target_len(lens[r]))
-                out[i] = seg
-                if cache is not None:
-                    cache.put(batch[r], seg)
+            emit(group, batch, lens, [n_phys] * len(group), enc, ad, ids)
     return out
 
 

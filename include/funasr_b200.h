@@ -95,6 +95,20 @@ FA_API int fa_front_half(fa_ctx* ctx, const float* audio_host, int batch, int64_
 FA_API int fa_front_half_dev(fa_ctx* ctx, const float* audio_dev, int batch, int64_t samples, const int64_t* ilens_host,
                       float* enc_dev, float* adaptor_dev, int32_t* ids_dev);
 
+/* ---- ragged batches: every segment at ITS OWN physical length ------------------------------------------------
+ * The unmasked CTC head makes a segment's ids depend on its physical (padded) length, so padding a short
+ * window up to a longer neighbour would change them: windows of different lengths could not share a batch.  Here row b of
+ * `audio` (row stride `samples`) is computed exactly as the reference computes a segment of ilens[b] valid samples fed at
+ * physical length phys[b] (ilens[b] <= phys[b] <= samples; nano_onnx.py:90-99 pads to max(len, 1 s) on the CPU provider):
+ * the padding-free row layout never materialises padded frames, and the head counts each segment's own
+ * frames(phys[b]) - frames(ilens[b]) zero frames as one key of that multiplicity.  Outputs keep the uniform
+ * [batch][frames(samples)] shapes; rows past a segment's valid frames are zero, ids past its own physical frames are -1.
+ * Needs a tensor-core precision mode. */
+FA_API int fa_front_half_ragged(fa_ctx* ctx, const float* audio_host, int batch, int64_t samples, const int64_t* ilens,
+                         const int64_t* phys, float* enc_host, float* adaptor_host, int32_t* ids_host);
+FA_API int fa_front_half_ragged_dev(fa_ctx* ctx, const float* audio_dev, int batch, int64_t samples, const int64_t* ilens_host,
+                             const int64_t* phys_host, float* enc_dev, float* adaptor_dev, int32_t* ids_dev);
+
 /* ---- embedding handoff ----------------------------------------------------------------
  * fa_front_half, except that of each segment's adaptor_output only the rows the LLM reads — [0, target_len), what
  * nano_onnx.py:131-133 slices out — leave the device, written straight to embd_rows[b] (host or device memory,

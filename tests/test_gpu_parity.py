@@ -192,6 +192,46 @@ def test_packed_execution_is_bit_identical_to_padded_execution(weights, consts, 
         padded.close()
 
 
+def test_ragged_batch_every_segment_at_its_own_physical_length(weights, planted_weights, consts):
+    """fa_front_half_ragged: the unmasked CTC head makes a segment's ids depend on its physical (padded) length,
+    so windows of different lengths could not share a batch without changing them.  In the padding-free layout every
+    segment keeps ITS OWN physical length: row b must equal the uniform call on that segment alone at phys[b] — enc and
+    adaptor bit for bit, ids identical — whatever else is in the batch, and match the oracle run at phys[b]."""
+    cases_ = [(7 * SR + 5, 8 * SR), (3 * SR, 3 * SR), (700, SR), (5 * SR - 77, 8 * SR + 333), (2 * SR + 1, 6 * SR), (8 * SR + 333, 8 * SR + 333)]
+    s_max = max(p for _, p in cases_)
+    batch = torch.stack([signals.padded(signals.structured(n, 60 + i), s_max) for i, (n, _) in enumerate(cases_)])
+    lens, phys = [n for n, _ in cases_], [p for _, p in cases_]
+    eng = FrontHalf(planted_weights, device=0, max_batch=len(cases_), max_samples=s_max, precision="bf16x3")
+    try:
+        enc, ad, ids = eng.front_half(batch.numpy(), lens, phys=phys)
+        for b, (n, p) in enumerate(cases_):
+            t = eng.frames(p)
+            e1, a1, i1 = eng.front_half(batch.numpy()[b:b + 1, :p], [n])
+            assert np.array_equal(enc[b, :t], e1[0]) and np.array_equal(ad[b, :t], a1[0]), f"row {b}"
+            assert not enc[b, t:].any() and not ad[b, t:].any()
+            assert np.array_equal(ids[b, :t], i1[0]), f"row {b}: {int((ids[b, :t] != i1[0]).sum())} ids differ from the uniform call"
+            assert (ids[b, t:] == -1).all()
+        for b in (0, 3, 4):
+            n, p = cases_[b]
+            enc_o, ad_o = O.encode_one(batch[b, :p], n, planted_weights, consts)
+            _act_close(enc[b, :eng.frames(p)], enc_o.numpy(), "bf16x3", f"ragged row{b} enc")
+            _check_ids(ids[b, :eng.frames(p)], O.ctc_logits_one(enc_o, planted_weights), "bf16x3", f"ragged row{b}")
+        d = eng.front_half_cuda(batch.cuda(), lens, phys=phys)
+        eng.sync()
+        assert np.array_equal(d[0].cpu().numpy(), enc) and np.array_equal(d[2].cpu().numpy(), ids)
+        with pytest.raises(RuntimeError):
+            eng.front_half(batch.numpy(), lens, phys=[n - 1 for n in lens])          # phys below the valid length
+    finally:
+        eng.close()
+    fp32 = FrontHalf(weights, device=0, max_batch=2, max_samples=2 * SR, precision="fp32")
+    try:
+        assert not fp32.supports_ragged
+        with pytest.raises(RuntimeError):
+            fp32.front_half(np.zeros((2, 2 * SR), np.float32), [SR, SR], phys=[SR, 2 * SR])
+    finally:
+        fp32.close()
+
+
 def test_more_segments_than_max_batch(engine):
     s = 2 * SR
     batch = np.stack([signals.white(s, i).numpy() for i in range(6)])     # max_batch is 4
