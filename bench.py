@@ -241,7 +241,8 @@ def make_plan(args, world: int, rank: int) -> "list[Plan]":
             # all of a rank's windows — the 16 s tail included — in evenly sized RAGGED batches: every window keeps its own
             # physical length (fa_front_half_ragged), as lookahead.run_file batches a file
             order = sorted(mine, key=lambda i: windows[i][0] - windows[i][1])
-            n_b = -(-len(order) // args.batch)
+            cap = args.batch + 1                         # 65 windows on one GPU: 33 + 32, not 22 + 22 + 21
+            n_b = -(-len(order) // cap)
             batches = []
             for k in range(n_b):
                 grp = order[k::n_b]
@@ -250,7 +251,7 @@ def make_plan(args, world: int, rank: int) -> "list[Plan]":
                 for r, i in enumerate(grp):
                     rows[r, :lens[r]] = base[windows[i][0]:windows[i][1]]
                 batches.append((rows.pin_memory(), lens, lens if min(lens) < max(lens) else None))
-            plans.append(Plan(batches, 3600.0, "strong", args.batch, s60, {"windows": len(windows), "windows_this_rank": len(mine)}))
+            plans.append(Plan(batches, 3600.0, "strong", cap, s60, {"windows": len(windows), "windows_this_rank": len(mine)}))
         elif args.workload == "config5":
             per = 256 // world
             batches = []

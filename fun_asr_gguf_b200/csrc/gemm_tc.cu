@@ -53,10 +53,16 @@ template <int NP, int TN = BN> struct Cfg {
 };
 
 // CTA-pair kernel: per CTA and stage, NP planes of (A 128 x 64 + W-half up to 128 x 64)
-template <int NP> struct Cfg2 {
+// F8: the e4m3 kernel's main loop is 2 k cycles per K = 512 tile, so its throughput is the epilogue's: SIXTEEN epilogue warps
+// (two 32-column chunks each instead of four: half the dependent chain per warp, twice the loads and stores in flight),
+// paid for with one operand stage (5 x 32 KB + 16 x 4 KB staging tiles)
+template <int NP, bool F8 = false> struct Cfg2 {
     static constexpr int kHalfWBytes = (BN / 2) * BK * 2;                    // 16 KB: this CTA's 128 rows of the W tile
     static constexpr int kStageBytes = NP * (kATileBytes + kHalfWBytes);      // 64 KB (NP=2) / 32 KB (NP=1)
-    static constexpr int kStages = NP == 2 ? 3 : 6;
+    static constexpr int kStages = NP == 2 ? 3 : (F8 ? 5 : 6);
+    static constexpr int kEpiWarps = F8 ? 16 : 8;
+    static constexpr int kThreads = 64 + 32 * kEpiWarps;
+    static constexpr int kStagingBytes = kEpiWarps * 4096;
     static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -128,10 +134,14 @@ __device__ __forceinline__ float ord2f_dev(int32_t o) { return __int_as_float(o 
 // everything that touches global memory goes through a 4 KB per-warp staging tile (XOR-swizzled,
 // conflict-free both ways) so that loads and stores are row-contiguous: 8 lanes cover one 128-byte
 // line instead of 32 lanes touching 32 different lines.
+template <int kEpiWarps = 8>
 __device__ __forceinline__ void epilogue_unit(const EpiParams& ep, const CUtensorMap* map_out, const CUtensorMap* map_pl,
                                               unsigned char* stg, bool& store_pending, int e, int lane, int m, int n, int row0,
                                               int n0, int nw, uint32_t tmem_acc, uint32_t bar_ready, uint32_t ready_parity) {
-    const int quarter = (e + 2) & 3, half = e >> 2;              // epilogue warps are warps 2..9: warp & 3 == (e + 2) & 3
+    // epilogue warps are warps 2..: warp & 3 == (e + 2) & 3 picks the TMEM lane quarter; e >> 2 the group of column chunks
+    constexpr int kCpw = 32 / kEpiWarps;                         // 32-column chunks per warp: 4 (8 warps) or 2 (16 warps)
+    constexpr bool kPrefetch = kEpiWarps == 8;                   // next chunk's residual one chunk ahead (16 warps: the other warps hide it)
+    const int quarter = (e + 2) & 3, half = (e >> 2) * kCpw / 4; // `half`: which 128 columns (the fused-argmax slots; 8 warps only)
     const int sub = lane >> 3, q8 = lane & 7;                    // fp32 staging: row sub+4i, 16-byte chunk q8
     const int row_base = row0 + quarter * 32;
     const int row = row_base + lane;
@@ -161,19 +171,20 @@ __device__ __forceinline__ void epilogue_unit(const EpiParams& ep, const CUtenso
             store_pending = false;
         }
     };
-    float4 rv[8], rv_next[8];
+    float4 rv[8], rv_next[kPrefetch ? 8 : 1];
+    const int c_first = (e >> 2) * kCpw;
     FA_GT(long long gt[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long g0 = clock64(); long long g1;)
-    load_resid(half * 4, rv);
+    load_resid(c_first, rv);
     mbar_wait(bar_ready, ready_parity);                          // the accumulator is complete
     tc_fence_after();
     FA_GT(g1 = clock64(); gt[0] += g1 - g0; g0 = g1;)
 #pragma unroll 1
-    for (int cc = 0; cc < 4; ++cc) {
-        const int c = half * 4 + cc;
+    for (int cc = 0; cc < kCpw; ++cc) {
+        const int c = c_first + cc;
         const int col0 = n0 + c * 32;
         if (c * 32 >= nw || col0 >= n) break;                    // warp-uniform
         any = true;
-        if (cc < 3) load_resid(c + 1, rv_next);
+        if constexpr (kPrefetch) { if (cc < kCpw - 1) load_resid(c + 1, rv_next); }
         // bias of the chunk's 32 columns: the same 8 vectors for every lane (broadcast loads)
         float bias[32];
         if (col0 + 32 <= n) {
@@ -323,13 +334,17 @@ __device__ __forceinline__ void epilogue_unit(const EpiParams& ep, const CUtenso
             store_pending = true;
             FA_GT(g1 = clock64(); gt[7] += g1 - g0; g0 = g1;)    // plane store: split, (acquire), smem write, fence, issue
         }
+        if constexpr (kPrefetch) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) rv[i] = rv_next[i];
+            for (int i = 0; i < 8; ++i) rv[i] = rv_next[i];
+        } else {
+            if (cc < kCpw - 1) load_resid(c + 1, rv);            // after this chunk's stores have been issued
+        }
     }
     FA_GT(if (ep.dbg && lane == 0) { for (int i = 0; i < 8; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(ep.dbg) + i, (unsigned long long)gt[i]);
                                       atomicAdd(reinterpret_cast<unsigned long long*>(ep.dbg) + 8, 1ull); })
     if (ep.cand_list && any && row < m) atomicMax(ep.cand_run_max + row, f2ord_dev(best));
-    if (ep.amax_val && half * 128 < nw) {
+    if (kEpiWarps == 8 && ep.amax_val && half * 128 < nw) {
         // one partial slot per (row, 128-column group): the two column halves of a 256-wide tile live in
         // different warps, and a half tile of the tail is exactly one group.  A group that lies wholly past N
         // (the last tile of the vocabulary) still gets its slot written — (-inf, none) — because the combine
@@ -549,16 +564,16 @@ __device__ __forceinline__ void unit_coords(int u, const Sched& s, int& mt, int&
 // floating point): a K-block is 128 elements = the same 128-byte rows, tcgen05.mma.kind::f8f6f4 takes K = 32 per
 // instruction, the per-output-channel weight scale is applied in the epilogue.  Everything else is the NP = 1 kernel.
 template <int NP, bool F8 = false>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((Cfg2<NP, F8>::kThreads), 1)
 k_gemm_tc2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
            const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_pl, int m, int n, int k,
            Sched sched, EpiParams ep) {
-    using C = Cfg2<NP>;
+    using C = Cfg2<NP, F8>;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t tiles_base = (raw + 1023u) & ~1023u;
     const uint32_t stg_base = tiles_base + C::kStages * C::kStageBytes;
-    const uint32_t bars = stg_base + kStagingBytes;
+    const uint32_t bars = stg_base + C::kStagingBytes;
     const uint32_t bar_full = bars, bar_empty = bars + 8 * C::kStages;
     const uint32_t bar_tfull = bars + 16 * C::kStages, bar_tempty = bar_tfull + 16;
     const uint32_t tmem_slot = bar_tempty + 16;
@@ -578,7 +593,7 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(bar_tfull + 8 * a, 1);      // multicast commit, in each CTA
-            mbar_init(bar_tempty + 8 * a, 16);    // used in the leader only: 8 epilogue warps of each CTA
+            mbar_init(bar_tempty + 8 * a, 2 * C::kEpiWarps);    // used in the leader only: the epilogue warps of both CTAs
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -694,8 +709,8 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
             unit_coords(u, sched, mt, n0, nw);
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            epilogue_unit(ep, &map_out, &map_pl, stg, store_pending, e, lane, m, n, (mt * 2 + rank) * BM, n0, nw, tmem_base + acc * BN,
-                          bar_tfull + 8 * acc, acc_phase);
+            epilogue_unit<C::kEpiWarps>(ep, &map_out, &map_pl, stg, store_pending, e, lane, m, n, (mt * 2 + rank) * BM, n0, nw,
+                                        tmem_base + acc * BN, bar_tfull + 8 * acc, acc_phase);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(leader_addr(bar_tempty + 8 * acc));
@@ -988,7 +1003,7 @@ void tc_init_device() {
     FA_CUDA(cudaFuncSetAttribute((k_gemm_tc<2, 64>), cudaFuncAttributeMaxDynamicSharedMemorySize, (Cfg<2, 64>::kSmemBytes)));
     FA_CUDA(cudaFuncSetAttribute(k_gemm_tc2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<1>::kSmemBytes));
     FA_CUDA(cudaFuncSetAttribute(k_gemm_tc2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<2>::kSmemBytes));
-    FA_CUDA(cudaFuncSetAttribute((k_gemm_tc2<1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<1>::kSmemBytes));
+    FA_CUDA(cudaFuncSetAttribute((k_gemm_tc2<1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (Cfg2<1, true>::kSmemBytes)));
     FA_CUDA(cudaFuncSetAttribute(k_gemm_tc2_ar, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgAR::kSmemBytes));
     int dev = 0;
     FA_CUDA(cudaGetDevice(&dev));
@@ -1179,7 +1194,9 @@ void launch_gemm_tc(const TcOperand& a, const TcOperand& w, int m, int n, int k,
         s.split_log2 = (rest > 0 && 2 * rest <= pairs) ? 1 : 0;
         s.total_units = s.full_units + (rest << s.split_log2);
         if (g_prof_on) { char tag[64]; snprintf(tag, sizeof tag, "fp8_n%d_k%d", n, k); prof_note_tag(tag); }
-        FA_LAUNCH((k_gemm_tc2<1, true>), 2 * pairs, kThreads, Cfg2<1>::kSmemBytes, st, a.map, w.map, map_out, map_pl, m, n, k, s, ep);
+        FA_REQUIRE(!ep.amax_val && !ep.cand_list, "the fp8 projection kernel has no vocabulary-argmax epilogue");
+        FA_LAUNCH((k_gemm_tc2<1, true>), 2 * pairs, (Cfg2<1, true>::kThreads), (Cfg2<1, true>::kSmemBytes), st, a.map, w.map, map_out,
+                  map_pl, m, n, k, s, ep);
         return;
     }
     const int force = gemm_kernel_override();
