@@ -705,10 +705,8 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, const __grid_constant
                 if (lane == 0 && !direct && wrow0 < qlen) {          // uniform layout: rows past the segment's end are clipped by the map
                     const int mrow = p.seg_off ? seg_row0 + wrow0 : wrow0, mseg = p.seg_off ? 0 : b;
 #pragma unroll
-                    for (int bx = 0; bx < DK / 64; ++bx) {
+                    for (int bx = 0; bx < DK / 64; ++bx)     // one store per 64-column box: the map's box spans both planes (hi tile, lo tile)
                         tma_store_4d(&map_out, stg_u32 + bx * 8192, h * DK + bx * 64, mrow, mseg, 0);
-                        if (p.ctx_lo) tma_store_4d(&map_out, stg_u32 + bx * 8192 + 4096, h * DK + bx * 64, mrow, mseg, 1);
-                    }
                     bulk_commit();
                 }
             } else {
@@ -765,7 +763,7 @@ CUtensorMap att_out_map(Planes out, int ldo, int d_model, int frames, int batch)
     FA_REQUIRE(plane_stride > 0 && plane_stride % 8 == 0, "attention output planes: lo must follow hi at a multiple of 8 elements");
     const cuuint64_t dims[4] = {(cuuint64_t)d_model, (cuuint64_t)frames, (cuuint64_t)batch, (cuuint64_t)(out.lo ? 2 : 1)};
     const cuuint64_t strides[3] = {(cuuint64_t)ldo * 2, (cuuint64_t)frames * ldo * 2, (cuuint64_t)plane_stride * 2};
-    const cuuint32_t box[4] = {64, 32, 1, 1};
+    const cuuint32_t box[4] = {64, 32, 1, (cuuint32_t)(out.lo ? 2 : 1)};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     CUtensorMap m;
     const CUresult r = g_att_encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out.hi, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,

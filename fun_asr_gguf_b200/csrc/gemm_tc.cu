@@ -291,22 +291,16 @@ __device__ __forceinline__ void epilogue_unit(const EpiParams& ep, const CUtenso
             FA_GT(g1 = clock64(); gt[6] += g1 - g0; g0 = g1;)    // fp32 store: smem write, fence, issue
         }
         if (ep.out_f8) {
-            // e4m3 (round to nearest even, saturating at +-448): a thread owns 32 consecutive bytes of its row; the 1 KB
-            // tile leaves as a tensor store like the other output forms (map_pl is the e4m3 map in this case; rows and
-            // columns past the matrix edge are clipped by it)
+            // e4m3 (round to nearest even, saturating at +-448): a thread owns 32 consecutive bytes of its row per chunk; the
+            // warp's chunks are adjacent columns, so they are staged side by side and leave as ONE tensor store after the last
+            // (map_pl is the e4m3 map in this case; rows and columns past the matrix edge are clipped by it)
             uint32_t w8[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) w8[j] = f32x4_to_e4m3(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            stg_acquire();
-            *reinterpret_cast<uint4*>(stg + lane * 32) = make_uint4(w8[0], w8[1], w8[2], w8[3]);
-            *reinterpret_cast<uint4*>(stg + lane * 32 + 16) = make_uint4(w8[4], w8[5], w8[6], w8[7]);
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-                tma_store_2d(map_pl, stg_s, col0, row_base);
-                bulk_commit();
-            }
-            store_pending = true;
+            if (cc == 0) stg_acquire();
+            unsigned char* d8 = stg + lane * (kCpw * 32) + cc * 32;
+            *reinterpret_cast<uint4*>(d8) = make_uint4(w8[0], w8[1], w8[2], w8[3]);
+            *reinterpret_cast<uint4*>(d8 + 16) = make_uint4(w8[4], w8[5], w8[6], w8[7]);
         }
         if (ep.out_hi) {
             if (col0 < ep.pl_col_scale_end) {                    // warp-uniform: the q columns of a fused q|k|v projection
@@ -327,8 +321,7 @@ __device__ __forceinline__ void epilogue_unit(const EpiParams& ep, const CUtenso
             fence_async_smem();
             __syncwarp();
             if (lane == 0) {
-                tma_store_3d(map_pl, stg_s, col0, row_base, 0);
-                if (ep.out_lo) tma_store_3d(map_pl, stg_s + 2048, col0, row_base, 1);
+                tma_store_3d(map_pl, stg_s, col0, row_base, 0);      // ONE store: the map's box spans both planes (hi tile, lo tile)
                 bulk_commit();
             }
             store_pending = true;
@@ -340,6 +333,15 @@ __device__ __forceinline__ void epilogue_unit(const EpiParams& ep, const CUtenso
         } else {
             if (cc < kCpw - 1) load_resid(c + 1, rv);            // after this chunk's stores have been issued
         }
+    }
+    if (ep.out_f8 && any) {
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            tma_store_2d(map_pl, stg_s, n0 + c_first * 32, row_base);
+            bulk_commit();
+        }
+        store_pending = true;
     }
     FA_GT(if (ep.dbg && lane == 0) { for (int i = 0; i < 8; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(ep.dbg) + i, (unsigned long long)gt[i]);
                                       atomicAdd(reinterpret_cast<unsigned long long*>(ep.dbg) + 8, 1ull); })
@@ -1061,12 +1063,12 @@ TcOperand tc_make_operand_f8(const uint8_t* base, int rows, int k, int64_t row_s
 namespace {
 // tensor map of an epilogue output: `rank`-D, 32 x 32 boxes, rows of one box 128 B (fp32) or 64 B (bf16) wide
 CUtensorMap make_store_map(CUtensorMapDataType dt, int elem_bytes, void* base, int rank, const cuuint64_t* dims,
-                           const cuuint64_t* strides_bytes, CUtensorMapSwizzle swz) {
+                           const cuuint64_t* strides_bytes, CUtensorMapSwizzle swz, int box_cols = 32, int box_planes = 1) {
     FA_REQUIRE(g_encode != nullptr, "tc_init_device() has not run");
     FA_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base must be 16-byte aligned");
     (void)elem_bytes;
     CUtensorMap map;
-    const cuuint32_t box[3] = {32, 32, 1};
+    const cuuint32_t box[3] = {(cuuint32_t)box_cols, 32, (cuuint32_t)box_planes};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = g_encode(&map, dt, (cuuint32_t)rank, base, dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                                 CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1162,16 +1164,18 @@ void launch_gemm_tc(const TcOperand& a, const TcOperand& w, int m, int n, int k,
         FA_REQUIRE(plane_stride > 0 && plane_stride % 8 == 0, "output planes must be hi then lo, a multiple of 8 elements apart");
         const cuuint64_t dims[3] = {(cuuint64_t)n, (cuuint64_t)m, (cuuint64_t)planes};
         const cuuint64_t strides[2] = {(cuuint64_t)e.ldp * 2, (cuuint64_t)plane_stride * 2};
-        map_pl = make_store_map(CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ep.out_hi, 3, dims, strides, CU_TENSOR_MAP_SWIZZLE_64B);
+        map_pl = make_store_map(CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ep.out_hi, 3, dims, strides, CU_TENSOR_MAP_SWIZZLE_64B, 32, planes);
     }
     // A gated launch whose gate is closed executes nothing: it is booked at 0 FLOP under its own key (the gate is
     // only known on the device; the second-chance vocabulary pass is the one gated launch and its gate is closed
     // unless a candidate list overflowed).
     if (ep.out_f8) {
-        FA_REQUIRE(!ep.out_hi, "a launch writes bf16 planes or e4m3, not both");
+        FA_REQUIRE(!ep.out_hi && !ep.out, "a launch writes e4m3 or the other output forms, not both (they share the staging tile)");
+        FA_REQUIRE(e.f8, "the e4m3 output form belongs to the fp8 projection kernel");
         const cuuint64_t dims[2] = {(cuuint64_t)n, (cuuint64_t)m};
         const cuuint64_t strides[1] = {(cuuint64_t)e.ld8};
-        map_pl = make_store_map(CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, ep.out_f8, 2, dims, strides, CU_TENSOR_MAP_SWIZZLE_NONE);
+        map_pl = make_store_map(CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, ep.out_f8, 2, dims, strides, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                32 * (32 / Cfg2<1, true>::kEpiWarps));      // the chunks of one epilogue warp side by side
     }
     prof_note_work(e.gate ? 0.0 : 2.0 * m * (double)n * k, 0.0);
     if (g_prof_on) {
