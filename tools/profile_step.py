@@ -24,11 +24,13 @@ def main():
     ap.add_argument("--precision", default="bf16x3")
     ap.add_argument("--breakdown", action="store_true", help="print per-kernel CUDA-event totals of one extra step")
     ap.add_argument("--per-launch", action="store_true", help="with --breakdown: also dump every launch")
+    ap.add_argument("--cuda-profiler", action="store_true", help="cudaProfilerStart/Stop around the timed steps (ncu --profile-from-start off)")
+    ap.add_argument("--mixed", action="store_true", help="BASELINE configs[2]: lengths randint(80 000, 960 001), seed 1234 (padding-free path)")
     args = ap.parse_args()
 
     import torch
     from fun_asr_gguf_b200 import FrontHalf, weights as Wm, engine as E
-    from tests import signals
+    from fun_asr_gguf_b200 import synth as signals
 
     s = int(args.seconds * 16000)
     dev = torch.device("cuda", 0)
@@ -40,10 +42,14 @@ def main():
     ad = torch.empty((args.batch, t, 1024), dtype=torch.float32, device=dev)
     ids = torch.empty((args.batch, t), dtype=torch.int32, device=dev)
     ilens = [s] * args.batch
+    if args.mixed:
+        g = torch.Generator().manual_seed(1234)
+        ilens = [min(int(v), s) for v in torch.randint(80_000, 960_001, (args.batch,), generator=g)]
+        for i, n in enumerate(ilens):
+            audio[i, n:] = 0
 
     def step():
-        eng.encode_cuda(audio, ilens, enc, ad)
-        eng.ctc_cuda(enc, ids)
+        eng.front_half_cuda(audio, ilens, enc, ad, ids)
 
     for _ in range(args.warmup):
         step()
@@ -51,6 +57,8 @@ def main():
     l0 = eng.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     import time
+    if args.cuda_profiler:
+        torch.cuda.profiler.start()
     e0.record()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -58,6 +66,8 @@ def main():
     enqueue_ms = (time.perf_counter() - t0) * 1e3 / max(args.steps, 1)
     e1.record()
     torch.cuda.synchronize()
+    if args.cuda_profiler:
+        torch.cuda.profiler.stop()
     ms = e0.elapsed_time(e1) / max(args.steps, 1)
     print(json.dumps({"batch": args.batch, "seconds": args.seconds, "ms_per_step": ms, "cpu_enqueue_ms_per_step": enqueue_ms,
                       "audio_s_per_s": args.batch * args.seconds / (ms * 1e-3),
