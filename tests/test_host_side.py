@@ -258,3 +258,43 @@ def test_sessions_survive_an_engine_rebuild(monkeypatch):
     assert len(built) == 2
     for t in (1, 17, 1001, 1034):
         assert Wm.lfr_frames(ort_shim.samples_for_frames(t)) == t and (t == 1 or Wm.lfr_frames(ort_shim.samples_for_frames(t) - 1) == t - 1)
+
+
+def test_lookahead_puts_every_window_of_a_file_into_ragged_batches(weights, consts):
+    """With an engine that takes per-segment physical lengths (fa_front_half_ragged), run_file batches ALL windows of a
+    file — the short tail included — instead of only windows of equal physical length, and hands every window back in
+    the shapes of its own physical length.  (Stand-in engine: the oracle run row by row at phys[b]; the CUDA engine's
+    ragged call is checked against that same definition in tests/test_gpu_parity.py.)"""
+    from fun_asr_gguf_b200 import lookahead
+    calls = []
+
+    class Ragged(_OracleEngine):
+        supports_ragged = True
+        max_batch = 3
+
+        def front_half(self, audio, ilens, phys=None):
+            calls.append((audio.shape, list(ilens), list(phys)))
+            b, s = audio.shape
+            t = Wm.lfr_frames(s)
+            enc, ad, ids = np.zeros((b, t, 512), np.float32), np.zeros((b, t, 1024), np.float32), np.full((b, t), -1, np.int32)
+            for r in range(b):
+                e, a = O.encode_one(torch.from_numpy(audio[r, :phys[r]]), ilens[r], self.w, self.c)
+                tp = e.shape[0]
+                enc[r, :tp], ad[r, :tp], ids[r, :tp] = e.numpy(), a.numpy(), O.ctc_ids_one(e, self.w).numpy()
+            return enc, ad, ids
+
+    sr = 16000
+    audio = signals.structured(7 * sr - 123, 5).numpy()
+    res = lookahead.run_file(Ragged(weights, consts), audio, segment_s=2.0, overlap_s=0.5)
+    windows = segments.segment_windows(audio.shape[0], 2.0, 0.5)
+    assert len(res) == len(windows) == 5 and len(calls) == 2                       # 5 windows, batches of <= 3: sizes 3 + 2
+    assert sorted(len(c[1]) for c in calls) == [2, 3] and all(c[2] != [c[2][0]] * len(c[2]) or len(set(c[2])) == 1 for c in calls)
+    assert any(len(set(c[2])) > 1 for c in calls)                                  # the tail shares a batch with full windows
+    for (a, b), r in zip(windows, res):
+        n_phys = lookahead.physical_samples(b - a)
+        fed = np.zeros(n_phys, np.float32)
+        fed[:b - a] = audio[a:b]
+        e_o, a_o = O.encode_one(torch.from_numpy(fed), b - a, weights, consts)
+        assert r.enc_output.shape == (1, Wm.lfr_frames(n_phys), 512) and r.n_phys == n_phys
+        assert np.array_equal(r.enc_output[0], e_o.numpy()) and np.array_equal(r.adaptor_output[0], a_o.numpy())
+        assert np.array_equal(r.ids[0], O.ctc_ids_one(e_o, weights).numpy())
