@@ -109,16 +109,17 @@ struct AttnParams {
     int ldo;
     int force_exact;                           // FUNASR_B200_ATTENTION_SHIFT=exact: every item in the exact (two-pass) mode
     int items;                                 // (segment, head, query tile) items of the launch
-    // packed rows (kernels.h Packing; all null for the uniform [batch][frames] layout): segment b is rows
-    // seg_off[b] .. seg_off[b] + kv_len[b] - 1, items are dealt over the segments in `order` (longest first)
-    const int* seg_off;
-    const int* order;
-    const int* tile_off;
+    // packed rows (kernels.h Packing; null for the uniform [batch][frames] layout): one entry per 128-query tile
+    // {first row of the segment, its length, tile index, segment}; item = tile * heads + head
+    const int4* tile_tab;
     const float* key_bias;                     // [batch] added to the score of each segment's last key (Packing::last_key_bias)
     long long* dbg;                            // tuning aid (FUNASR_B200_ATTN_TIMING): cycles the MMA warp waits, by cause
 };
 
-template <int DK>
+// PK: packed rows (kernels.h Packing).  A template parameter so that the uniform-layout instance — every launch of a
+// batch of equal-length segments — carries none of the packed path's code (item search, straddling output warps, the
+// CTC head's key multiplicity).
+template <int DK, bool PK>
 __global__ void __launch_bounds__(kAttThreads, 1)
 k_attention_tc(const __grid_constant__ CUtensorMap map_kv, const __grid_constant__ CUtensorMap map_out, AttnParams p) {
     using C = ACfg<DK>;
@@ -170,20 +171,12 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, const __grid_constant
 
     // item -> (segment b, head h, query tile qt); key tiles n; first row of the segment and its query count
     auto decode = [&](int item, int& b, int& h, int& qt, int& n, int& klen, int& row0, int& qlen) {
-        if (p.seg_off) {
-            // packed: the items of the k-th longest segment start at heads * tile_off[k]
-            int lo = 0, hi = p.batch;                        // invariant: tile_off[lo] * heads <= item < tile_off[hi] * heads
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (p.tile_off[mid] * p.heads <= item) lo = mid; else hi = mid;
-            }
-            const int t0 = p.tile_off[lo], qtk = p.tile_off[lo + 1] - t0, local = item - t0 * p.heads;
-            h = local / qtk;
-            qt = local - h * qtk;
-            b = p.order[lo];
-            klen = p.kv_len[b];
+        if constexpr (PK) {
+            const int t = item / p.heads;
+            h = item - t * p.heads;
+            const int4 e = __ldg(p.tile_tab + t);
+            row0 = e.x; klen = e.y; qt = e.z; b = e.w;
             qlen = klen;
-            row0 = p.seg_off[b];
         } else {
             qt = item % q_tiles;
             const int bh = item / q_tiles;
@@ -504,7 +497,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, const __grid_constant
                     uint32_t s[32];
                     tc_ld32(ts, s);
                     tc_wait_ld();
-                    if (p.key_bias && j == n - 1 && klen - 1 >= kbase && klen - 1 < kbase + 32) {   // warp-uniform, once per item
+                    if (PK && p.key_bias && j == n - 1 && klen - 1 >= kbase && klen - 1 < kbase + 32) {   // warp-uniform, once per item
                         // the segment's last key stands for n_pad identical keys: weight n_pad * exp2(s) = exp2(s + log2 n_pad)
                         const int at = klen - 1 - kbase;
                         const float kb = p.key_bias[b];
@@ -662,7 +655,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, const __grid_constant
                 // packed rows: the store map cannot clip at the end of a segment (the next segment's rows follow), so a
                 // warp whose 32 rows straddle the end writes its valid rows with plain stores (once per segment and head)
                 const int wrow0 = qt * QT + quarter * 32;
-                const bool direct = p.seg_off != nullptr && wrow0 + 32 > qlen;
+                const bool direct = PK && wrow0 + 32 > qlen;
                 if (lane == 0) bulk_wait_read0();                    // the previous item's stores have read the tiles (an item ago)
                 __syncwarp();
 #pragma unroll 1
@@ -703,7 +696,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap map_kv, const __grid_constant
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0 && !direct && wrow0 < qlen) {          // uniform layout: rows past the segment's end are clipped by the map
-                    const int mrow = p.seg_off ? seg_row0 + wrow0 : wrow0, mseg = p.seg_off ? 0 : b;
+                    const int mrow = PK ? seg_row0 + wrow0 : wrow0, mseg = PK ? 0 : b;
 #pragma unroll
                     for (int bx = 0; bx < DK / 64; ++bx)     // one store per 64-column box: the map's box spans both planes (hi tile, lo tile)
                         tma_store_4d(&map_out, stg_u32 + bx * 8192, h * DK + bx * 64, mrow, mseg, 0);
@@ -782,8 +775,10 @@ void attention_tc_init_device() {
         FA_REQUIRE(fn != nullptr && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available in this driver");
         g_att_encode = reinterpret_cast<EncodeTiledFn>(fn);
     });
-    FA_CUDA(cudaFuncSetAttribute(k_attention_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, ACfg<128>::kSmemBytes));
-    FA_CUDA(cudaFuncSetAttribute(k_attention_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ACfg<64>::kSmemBytes));
+    FA_CUDA(cudaFuncSetAttribute((k_attention_tc<128, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, ACfg<128>::kSmemBytes));
+    FA_CUDA(cudaFuncSetAttribute((k_attention_tc<64, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, ACfg<64>::kSmemBytes));
+    FA_CUDA(cudaFuncSetAttribute((k_attention_tc<128, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, ACfg<128>::kSmemBytes));
+    FA_CUDA(cudaFuncSetAttribute((k_attention_tc<64, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, ACfg<64>::kSmemBytes));
     int dev = 0;
     FA_CUDA(cudaGetDevice(&dev));
     FA_CUDA(cudaDeviceGetAttribute(&g_att_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -811,7 +806,7 @@ void launch_attention_tc(Planes qkv, int64_t plane_stride, int ld, int d_model, 
     if (ctx_pl.hi && !ctx_f32) map_out = pk ? att_out_map(ctx_pl, ldo, d_model, pk->total_rows, 1) : att_out_map(ctx_pl, ldo, d_model, frames, batch);
     const int items = pk ? heads * pk->total_tiles : batch * heads * cdiv(frames, QT);
     p.items = items;
-    if (pk) { p.seg_off = pk->seg_off; p.order = pk->order; p.tile_off = pk->tile_off; p.key_bias = pk->last_key_bias; }
+    if (pk) { p.tile_tab = pk->tile_tab; p.key_bias = pk->last_key_bias; }
     int grid = items < g_att_sms ? items : g_att_sms;
     if (const char* e = getenv("FUNASR_B200_ATT_SMS")) { const int v = atoi(e); if (v > 0 && v < grid) grid = v; }   // tuning aid: fewer CTAs
     // the repeat bitmap holds one bit per item of a CTA's sequence; more would spill into the barriers behind it
@@ -826,9 +821,11 @@ void launch_attention_tc(Planes qkv, int64_t plane_stride, int ld, int d_model, 
     prof_note_work(pk ? 4.0 * heads * pk->sum_len_sq * dk : 4.0 * batch * heads * (double)frames * frames * dk, 0.0);
     if (g_prof_on) prof_note_tag(dk == 128 ? "dk128" : "dk64");
     if (dk == 128) {
-        FA_LAUNCH(k_attention_tc<128>, grid, kAttThreads, ACfg<128>::kSmemBytes, st, mkv.map, map_out, p);
+        if (pk) FA_LAUNCH((k_attention_tc<128, true>), grid, kAttThreads, ACfg<128>::kSmemBytes, st, mkv.map, map_out, p);
+        else FA_LAUNCH((k_attention_tc<128, false>), grid, kAttThreads, ACfg<128>::kSmemBytes, st, mkv.map, map_out, p);
     } else {
-        FA_LAUNCH(k_attention_tc<64>, grid, kAttThreads, ACfg<64>::kSmemBytes, st, mkv.map, map_out, p);
+        if (pk) FA_LAUNCH((k_attention_tc<64, true>), grid, kAttThreads, ACfg<64>::kSmemBytes, st, mkv.map, map_out, p);
+        else FA_LAUNCH((k_attention_tc<64, false>), grid, kAttThreads, ACfg<64>::kSmemBytes, st, mkv.map, map_out, p);
     }
     if (timing) {       // tuning aid only: synchronises
         std::vector<long long> h((size_t)grid * 16);

@@ -382,7 +382,10 @@ void Context::finalize() {
         logits_.alloc((size_t)logits_rows_ * vocab_ * 4);
     }
     // n_valid, t_valid, target_len, seg_off[B+1], order[B], tile_off[B+1]; CTC head: seg_off[B+1], tile_off[B+1], len[B], bias[B]
-    len_ints_ = 11 * max_batch_ + 4;             // + t_phys[B] (ragged batches)
+    // + t_phys[B] (ragged batches); then, 16-byte aligned, the two attention tile tables (encoder/adaptor, CTC head)
+    max_tiles_ = max_batch_ * (cdiv(t_max_, 128) + 1);
+    tab_off_ = (11 * max_batch_ + 4 + 3) / 4 * 4;
+    len_ints_ = tab_off_ + 2 * 4 * max_tiles_;
     lens_.alloc((size_t)len_ints_ * sizeof(int));
     d_nvalid_ = lens_.as<int>();
     d_tvalid_ = d_nvalid_ + max_batch_;
@@ -616,12 +619,17 @@ void Context::stage_lengths(int batch, int64_t s_phys, const int64_t* h_ilens, b
         // attention items are dealt round-robin over the CTAs: longest segments first, so that every CTA's share
         // mixes long and short items (the cost of an item is proportional to its segment's length)
         std::stable_sort(h_order, h_order + batch, [&](int a, int b) { return h_tv[a] > h_tv[b]; });
+        int* h_tab = hl + tab_off_;                                   // int4 per query tile: {row0, len, tile, segment}
         int tiles = 0;
-        for (int k = 0; k < batch; ++k) { h_tile[k] = tiles; tiles += cdiv(h_tv[h_order[k]], 128); }
-        h_tile[batch] = tiles;
+        for (int k = 0; k < batch; ++k) {
+            const int b = h_order[k];
+            for (int qt = 0; qt < cdiv(h_tv[b], 128); ++qt, ++tiles) {
+                h_tab[4 * tiles] = h_off[b]; h_tab[4 * tiles + 1] = h_tv[b]; h_tab[4 * tiles + 2] = qt; h_tab[4 * tiles + 3] = b;
+            }
+        }
+        (void)h_tile;
         pk_.seg_off = d_nvalid_ + 3 * max_batch_;
-        pk_.order = pk_.seg_off + max_batch_ + 1;
-        pk_.tile_off = pk_.order + max_batch_;
+        pk_.tile_tab = reinterpret_cast<const int4*>(d_nvalid_ + tab_off_);
         pk_.total_rows = total; pk_.total_tiles = tiles; pk_.max_len = longest; pk_.sum_len_sq = sq;
         // the CTC head's rows: valid frames, then one row standing for the segment's frames - t_valid zero-padded frames
         int total_c = 0, tiles_c = 0;
@@ -635,13 +643,18 @@ void Context::stage_lengths(int batch, int64_t s_phys, const int64_t* h_ilens, b
             sq_c += (double)h_len_c[b] * h_len_c[b];
         }
         h_off_c[batch] = total_c;
-        for (int k = 0; k < batch; ++k) { h_tile_c[k] = tiles_c; tiles_c += cdiv(h_len_c[h_order[k]], 128); }
-        h_tile_c[batch] = tiles_c;
+        int* h_tab_c = h_tab + 4 * max_tiles_;
+        for (int k = 0; k < batch; ++k) {
+            const int b = h_order[k];
+            for (int qt = 0; qt < cdiv(h_len_c[b], 128); ++qt, ++tiles_c) {
+                h_tab_c[4 * tiles_c] = h_off_c[b]; h_tab_c[4 * tiles_c + 1] = h_len_c[b]; h_tab_c[4 * tiles_c + 2] = qt; h_tab_c[4 * tiles_c + 3] = b;
+            }
+        }
+        (void)h_tile_c;
         pk_ctc_ = Packing{};
-        pk_ctc_.order = pk_.order;
-        pk_ctc_.seg_off = pk_.tile_off + max_batch_ + 1;
-        pk_ctc_.tile_off = pk_ctc_.seg_off + max_batch_ + 1;
-        d_len_ctc_ = pk_ctc_.tile_off + max_batch_ + 1;
+        pk_ctc_.seg_off = d_nvalid_ + (h_off_c - hl);
+        pk_ctc_.tile_tab = pk_.tile_tab + max_tiles_;
+        d_len_ctc_ = d_nvalid_ + (h_len_c - hl);
         pk_ctc_.last_key_bias = reinterpret_cast<const float*>(d_len_ctc_ + max_batch_);
         if (h_phys) d_tphys_ = d_len_ctc_ + 2 * max_batch_;
         pk_ctc_.total_rows = total_c; pk_ctc_.total_tiles = tiles_c; pk_ctc_.max_len = longest + 1; pk_ctc_.sum_len_sq = sq_c;

@@ -192,6 +192,7 @@ private:
     bool fused_ctc_next_ = false;             // the CTC head follows in this call: encoder_graph prepares its packed input
     Act ctc_packed_input() const;
     bool ctc_packed_ready_ = false;           // encoder_graph left the head's packed input in encpl_ / enc8_
+    int max_tiles_ = 0, tab_off_ = 0;         // attention tile tables inside the staged block (kernels.h Packing::tile_tab)
     int len_ints_ = 0;           // ints per staging slot: 3 length vectors + seg_off, order, tile_off (+ the head's tables)
     const Packing* packing() const { return packed_ ? &pk_ : nullptr; }
     int enc_rows(int batch, int frames) const { return packed_ ? pk_.total_rows : batch * frames; }

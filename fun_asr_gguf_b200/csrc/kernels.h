@@ -18,8 +18,9 @@ void tc_init_device();
 // reference does not define as zero.  All arrays live in device memory and are staged per call.
 struct Packing {
     const int* seg_off = nullptr;    // [batch + 1] first packed row of each segment
-    const int* order = nullptr;      // [batch] segments by decreasing length: the order attention items are dealt in
-    const int* tile_off = nullptr;   // [batch + 1] prefix sums of 128-query tiles, in `order`
+    // [total_tiles] one entry per 128-query tile, longest segments first (the order attention items are dealt in, so that
+    // every CTA's share mixes long and short items): {first packed row of the segment, its length, tile index, segment}
+    const int4* tile_tab = nullptr;
     int total_rows = 0, total_tiles = 0, max_len = 0;
     double sum_len_sq = 0.0;         // sum of t_valid^2: attention FLOP accounting
     // CTC head only (SURVEY §7 hard part 2): [batch] log2 of the multiplicity of each segment's LAST key.  The head is
