@@ -1011,6 +1011,10 @@ void Context::test_linear(const float* a, const float* w, const float* bias, con
     if (resid) { dr.alloc((size_t)m * n * 4); FA_CUDA(cudaMemcpy(dr.p, resid, dr.bytes, cudaMemcpyHostToDevice)); }
     Epilogue e;
     e.bias = db.as<float>(); e.resid = dr.as<float>(); e.ldr = n; e.relu = relu != 0; e.out_f32 = dout.as<float>(); e.ldc = n;
+    if (resid && getenv("FUNASR_B200_TEST_INPLACE")) {      // the engine's form: the residual is the output buffer (x += ...)
+        FA_CUDA(cudaMemcpy(dout.p, resid, dout.bytes, cudaMemcpyHostToDevice));
+        e.resid = dout.as<float>();
+    }
     const int ldp = precision == kFp8 ? (n + 15) / 16 * 16 : (n + 7) / 8 * 8;
     if (out_planes_sum && getenv("FUNASR_B200_TEST_NO_F32")) e.out_f32 = nullptr;     // timing aid: the engine's planes-only epilogue
     if (out_planes_sum && precision != kFp8) {

@@ -93,6 +93,7 @@ struct EpiParams {
     int ldr, ldc, ldp, relu, n_slots;            // n_slots: 128-column groups of N (fused argmax partials)
     float pl_col_scale;
     int pl_col_scale_end, f32_col_begin;
+    int reduce_add;                              // the residual IS the fp32 output (x += ...): added by a tensor reduction, never read
     long long* dbg;                              // tuning aid (-DFA_GEMM_TIMING, FUNASR_B200_GEMM_TIMING=1): per-phase cycles
 };
 
@@ -153,7 +154,7 @@ __device__ __forceinline__ void epilogue_unit(const EpiParams& ep, const CUtenso
     // their use — the first chunk's before the accumulator is even complete — so the loads never stall the tile
     auto load_resid = [&](int c, float4 (&rv)[8]) {
         const int col0 = n0 + c * 32;
-        const bool live = ep.resid && c * 32 < nw && col0 < n;
+        const bool live = ep.resid && !ep.reduce_add && c * 32 < nw && col0 < n;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int rr = row_base + sub + 4 * i, cq = col0 + q8 * 4;
@@ -249,7 +250,7 @@ __device__ __forceinline__ void epilogue_unit(const EpiParams& ep, const CUtenso
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
         }
-        if (ep.resid) {
+        if (ep.resid && !ep.reduce_add) {
             FA_GT(g1 = clock64(); gt[3] += g1 - g0; g0 = g1;)    // bias add etc.
             stg_acquire();
             FA_GT(g1 = clock64(); gt[4] += g1 - g0; g0 = g1;)    // wait: previous store has read the staging tile
@@ -284,7 +285,10 @@ __device__ __forceinline__ void epilogue_unit(const EpiParams& ep, const CUtenso
             fence_async_smem();
             __syncwarp();
             if (lane == 0) {
-                tma_store_2d(map_out, stg_s, col0, row_base);
+                // x += tile: the residual stream is updated in place by the memory system (no residual read in this
+                // kernel; same bits as adding in registers: one fp32 round-to-nearest add per element, each element once)
+                if (ep.reduce_add) tma_reduce_add_2d(map_out, stg_s, col0, row_base);
+                else tma_store_2d(map_out, stg_s, col0, row_base);
                 bulk_commit();
             }
             store_pending = true;

@@ -330,6 +330,23 @@ def test_fsmn_streaming_kernel_matches_the_strip_kernel_bit_for_bit(raw, monkeyp
     assert rel_err(got, conv + vm + torch.from_numpy(resid).double()) <= 2e-6
 
 
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16", "fp8"])
+@pytest.mark.parametrize("m,n,k", [(300, 512, 512), (1001, 512, 2048), (2100, 1024, 256), (77, 512, 128)])
+def test_in_place_residual_is_a_tensor_reduction_with_the_same_bits(raw, gemm_kernel, monkeypatch, precision, m, n, k):
+    """x = x + A W^T + b with the residual being the output buffer (the out-projection and FFN 2 of every layer): the
+    epilogue does not read x, it hands acc + bias to a tensor REDUCTION (cp.reduce.async.bulk.tensor .add) and the memory
+    system adds it to x.  One fp32 round-to-nearest add per element, each element exactly once: the result must be
+    bit-identical to the read-add-store epilogue that a separate residual buffer takes."""
+    if precision == "fp8" and gemm_kernel == "1cta":
+        pytest.skip("the fp8 projections always run on the CTA-pair kernel")
+    a, w = _rand((m, k), 21), _rand((n, k), 22, k ** -0.5)
+    bias, resid = _rand((n,), 23), _rand((m, n), 24)
+    separate = raw.linear(a, w, bias, resid=resid, precision=precision)
+    monkeypatch.setenv("FUNASR_B200_TEST_INPLACE", "1")
+    in_place = raw.linear(a, w, bias, resid=resid, precision=precision)
+    assert np.array_equal(separate, in_place)
+
+
 # ------------------------------------------------------------------------------------ fp8 speed mode (SURVEY §8f-4)
 
 def _e4m3(x: torch.Tensor) -> torch.Tensor:
