@@ -103,6 +103,7 @@ class OrtValue:
 
 _engines: Dict[tuple, "object"] = {}
 _lock = threading.Lock()
+_run_lock = threading.RLock()          # serialises session calls on the shared context (and an engine swap against a running call)
 
 
 def _find_checkpoint(model_path: str) -> Optional[str]:
@@ -241,7 +242,8 @@ class InferenceSession:
                 hit = lookahead.cache().encoder_lookup(audio.reshape(s), int(ilens[0]))
                 if hit is not None:
                     return {"enc_output": hit.enc_output, "adaptor_output": hit.adaptor_output}
-            enc, ad = _engine_for(self._path, min_samples=s).encode(audio.reshape(b, s).astype(np.float32, copy=False), ilens.tolist())
+            with _run_lock:          # one context serves both sessions: one call at a time (ORT sessions are re-entrant)
+                enc, ad = _engine_for(self._path, min_samples=s).encode(audio.reshape(b, s).astype(np.float32, copy=False), ilens.tolist())
             return {"enc_output": enc, "adaptor_output": ad}
         if "enc_output" not in feed:
             raise ValueError("Required input 'enc_output' is missing")
@@ -253,8 +255,9 @@ class InferenceSession:
                 return {"indices": hit.ids}
         if enc.ndim != 3 or enc.shape[2] != W.D_ENC:
             raise ValueError(f"enc_output must be (batch, frames, {W.D_ENC}); got {enc.shape}")
-        eng = _engine_for(self._path, min_samples=samples_for_frames(enc.shape[1]))
-        return {"indices": eng.ctc(enc.astype(np.float32, copy=False))}
+        with _run_lock:
+            eng = _engine_for(self._path, min_samples=samples_for_frames(enc.shape[1]))
+            return {"indices": eng.ctc(enc.astype(np.float32, copy=False))}
 
     def run(self, output_names, input_feed: Dict[str, np.ndarray], run_options=None):
         return self._select(output_names, self._run(dict(input_feed)))
