@@ -381,10 +381,10 @@ void Context::finalize() {
         logits_rows_ = (int)std::min<size_t>(M, 2048);
         logits_.alloc((size_t)logits_rows_ * vocab_ * 4);
     }
-    // n_valid, t_valid, target_len, seg_off[B+1], order[B], tile_off[B+1]; CTC head: seg_off[B+1], tile_off[B+1], len[B], bias[B]
-    // + t_phys[B] (ragged batches); then, 16-byte aligned, the two attention tile tables (encoder/adaptor, CTC head)
+    // the staged block (layout at stage_lengths): nine B-sized vectors + two (B+1)-sized prefix arrays' extra entries,
+    // then, 16-byte aligned, the two attention tile tables (encoder/adaptor, CTC head)
     max_tiles_ = max_batch_ * (cdiv(t_max_, 128) + 1);
-    tab_off_ = (11 * max_batch_ + 4 + 3) / 4 * 4;
+    tab_off_ = (8 * max_batch_ + 2 + 3) / 4 * 4;
     len_ints_ = tab_off_ + 2 * 4 * max_tiles_;
     lens_.alloc((size_t)len_ints_ * sizeof(int));
     d_nvalid_ = lens_.as<int>();
@@ -574,20 +574,24 @@ void Context::projector(const Projector& P, const Act& in, int batch, int frames
 
 // ------------------------------------------------------------------------------------ graphs
 
+// Per-call lengths and packing tables, staged in one pinned block and uploaded with one copy.  Layout of the block
+// (ints; B = max_batch_): n_valid[B] | t_valid[B] | target_len[B] | seg_off[B+1] | ctc seg_off[B+1] | ctc len[B] |
+// ctc key bias[B] (float) | t_phys[B] | pad to 16 bytes | tile table[max_tiles_] (int4) | ctc tile table[max_tiles_] (int4)
 void Context::stage_lengths(int batch, int64_t s_phys, const int64_t* h_ilens, bool allow_packed, const int64_t* h_phys) {
     const int slot = len_next_;
     len_next_ = (len_next_ + 1) % kLenSlots;
     FA_CUDA(cudaEventSynchronize(len_ev_[slot]));
+    const int B = max_batch_;
     int* hl = h_lens_ + (size_t)slot * len_ints_;
-    int* h_tv = hl + max_batch_;
-    int* h_off = hl + 3 * max_batch_;            // [B+1]
-    int* h_order = h_off + max_batch_ + 1;       // [B]
-    int* h_tile = h_order + max_batch_;          // [B+1]
-    int* h_off_c = h_tile + max_batch_ + 1;      // [B+1]  CTC head packing
-    int* h_tile_c = h_off_c + max_batch_ + 1;    // [B+1]
-    int* h_len_c = h_tile_c + max_batch_ + 1;    // [B]
-    float* h_bias_c = reinterpret_cast<float*>(h_len_c + max_batch_);     // [B]
-    int* h_tphys = h_len_c + 2 * max_batch_;     // [B]
+    int* h_tv = hl + B;
+    int* h_off = hl + 3 * B;
+    int* h_off_c = h_off + B + 1;
+    int* h_len_c = h_off_c + B + 1;
+    float* h_bias_c = reinterpret_cast<float*>(h_len_c + B);
+    int* h_tphys = h_len_c + 2 * B;
+    int* h_tab = hl + tab_off_;
+    int* h_tab_c = h_tab + 4 * max_tiles_;
+    const int* d0 = d_nvalid_;
     const int frames = lfr_frames_of(s_phys);
     int total = 0, longest = 0;
     double sq = 0.0;
@@ -598,12 +602,11 @@ void Context::stage_lengths(int batch, int64_t s_phys, const int64_t* h_ilens, b
         h_tphys[b] = h_phys ? lfr_frames_of(h_phys[b]) : frames;
         hl[b] = (int)nv;
         h_tv[b] = lfr_frames_of(nv);
-        hl[2 * max_batch_ + b] = target_len_of(nv);
+        hl[2 * B + b] = target_len_of(nv);
         h_off[b] = total;
         total += h_tv[b];
         longest = std::max(longest, h_tv[b]);
         sq += (double)h_tv[b] * h_tv[b];
-        h_order[b] = b;
     }
     h_off[batch] = total;
     // Packed execution only pays (and only differs) when the batch holds padded frames
@@ -615,27 +618,31 @@ void Context::stage_lengths(int batch, int64_t s_phys, const int64_t* h_ilens, b
         packed_ = true;
     }
     d_tphys_ = nullptr;
+    ctc_packed_ready_ = false;
     if (packed_) {
         // attention items are dealt round-robin over the CTAs: longest segments first, so that every CTA's share
         // mixes long and short items (the cost of an item is proportional to its segment's length)
-        std::stable_sort(h_order, h_order + batch, [&](int a, int b) { return h_tv[a] > h_tv[b]; });
-        int* h_tab = hl + tab_off_;                                   // int4 per query tile: {row0, len, tile, segment}
-        int tiles = 0;
-        for (int k = 0; k < batch; ++k) {
-            const int b = h_order[k];
-            for (int qt = 0; qt < cdiv(h_tv[b], 128); ++qt, ++tiles) {
-                h_tab[4 * tiles] = h_off[b]; h_tab[4 * tiles + 1] = h_tv[b]; h_tab[4 * tiles + 2] = qt; h_tab[4 * tiles + 3] = b;
-            }
-        }
-        (void)h_tile;
-        pk_.seg_off = d_nvalid_ + 3 * max_batch_;
-        pk_.tile_tab = reinterpret_cast<const int4*>(d_nvalid_ + tab_off_);
-        pk_.total_rows = total; pk_.total_tiles = tiles; pk_.max_len = longest; pk_.sum_len_sq = sq;
-        // the CTC head's rows: valid frames, then one row standing for the segment's frames - t_valid zero-padded frames
-        int total_c = 0, tiles_c = 0;
+        std::vector<int> order(batch);
+        for (int b = 0; b < batch; ++b) order[b] = b;
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return h_tv[x] > h_tv[y]; });
+        auto fill_table = [&](int* tab, const int* off, const int* len) {       // int4 per query tile: {row0, len, tile, segment}
+            int tiles = 0;
+            for (int b : order)
+                for (int qt = 0; qt < cdiv(len[b], 128); ++qt, ++tiles) {
+                    tab[4 * tiles] = off[b]; tab[4 * tiles + 1] = len[b]; tab[4 * tiles + 2] = qt; tab[4 * tiles + 3] = b;
+                }
+            return tiles;
+        };
+        pk_ = Packing{};
+        pk_.seg_off = d0 + (h_off - hl);
+        pk_.tile_tab = reinterpret_cast<const int4*>(d0 + tab_off_);
+        pk_.total_rows = total; pk_.total_tiles = fill_table(h_tab, h_off, h_tv); pk_.max_len = longest; pk_.sum_len_sq = sq;
+        // the CTC head's rows: valid frames, then ONE row standing for all of the segment's zero-padded frames (counted
+        // at the segment's own physical length in a ragged batch), whose key weighs n_pad in every softmax
+        int total_c = 0;
         double sq_c = 0.0;
         for (int b = 0; b < batch; ++b) {
-            const int n_pad = h_tphys[b] - h_tv[b];        // zero-padded frames of the segment at ITS physical length
+            const int n_pad = h_tphys[b] - h_tv[b];
             h_len_c[b] = h_tv[b] + (n_pad > 0 ? 1 : 0);
             h_bias_c[b] = n_pad > 1 ? std::log2((float)n_pad) : 0.f;
             h_off_c[b] = total_c;
@@ -643,23 +650,15 @@ void Context::stage_lengths(int batch, int64_t s_phys, const int64_t* h_ilens, b
             sq_c += (double)h_len_c[b] * h_len_c[b];
         }
         h_off_c[batch] = total_c;
-        int* h_tab_c = h_tab + 4 * max_tiles_;
-        for (int k = 0; k < batch; ++k) {
-            const int b = h_order[k];
-            for (int qt = 0; qt < cdiv(h_len_c[b], 128); ++qt, ++tiles_c) {
-                h_tab_c[4 * tiles_c] = h_off_c[b]; h_tab_c[4 * tiles_c + 1] = h_len_c[b]; h_tab_c[4 * tiles_c + 2] = qt; h_tab_c[4 * tiles_c + 3] = b;
-            }
-        }
-        (void)h_tile_c;
         pk_ctc_ = Packing{};
-        pk_ctc_.seg_off = d_nvalid_ + (h_off_c - hl);
+        pk_ctc_.seg_off = d0 + (h_off_c - hl);
         pk_ctc_.tile_tab = pk_.tile_tab + max_tiles_;
-        d_len_ctc_ = d_nvalid_ + (h_len_c - hl);
-        pk_ctc_.last_key_bias = reinterpret_cast<const float*>(d_len_ctc_ + max_batch_);
-        if (h_phys) d_tphys_ = d_len_ctc_ + 2 * max_batch_;
-        pk_ctc_.total_rows = total_c; pk_ctc_.total_tiles = tiles_c; pk_ctc_.max_len = longest + 1; pk_ctc_.sum_len_sq = sq_c;
+        pk_ctc_.last_key_bias = reinterpret_cast<const float*>(d0 + (h_len_c - hl) + B);
+        pk_ctc_.total_rows = total_c; pk_ctc_.total_tiles = fill_table(h_tab_c, h_off_c, h_len_c); pk_ctc_.max_len = longest + 1;
+        pk_ctc_.sum_len_sq = sq_c;
+        d_len_ctc_ = d0 + (h_len_c - hl);
+        if (h_phys) d_tphys_ = d0 + (h_tphys - hl);
     }
-    ctc_packed_ready_ = false;
     FA_CUDA(cudaMemcpyAsync(lens_.p, hl, (size_t)len_ints_ * sizeof(int), cudaMemcpyHostToDevice, stream_));
     FA_CUDA(cudaEventRecord(len_ev_[slot], stream_));
 }
