@@ -78,8 +78,8 @@ def load() -> C.CDLL:
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError if the .so lacks a declared symbol
         fn.restype, fn.argtypes = res, args
-    if lib.fa_abi_version() != 1:
-        raise RuntimeError(f"ABI mismatch: library reports {lib.fa_abi_version()}, binding expects 1")
+    if lib.fa_abi_version() != 2:
+        raise RuntimeError(f"ABI mismatch: library reports {lib.fa_abi_version()}, binding expects 2")
     _lib = lib
     return lib
 

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define FA_ABI_VERSION 1
+#define FA_ABI_VERSION 2 /* 2: + fa_front_half_dev, fa_front_half_ragged(_dev), FA_PREC_FP8 (additions only) */
 
 #if defined(__GNUC__)
 #define FA_API __attribute__((visibility("default")))

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     assert declared and declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.fa_abi_version() == 1
+    assert lib.fa_abi_version() == 2
 
 
 def test_shape_helpers_match_reference_arithmetic():
