@@ -25,6 +25,11 @@ ACT_TOL = {"fp32": 2e-4, "bf16x3": 3e-4}
 # activation tolerance, i.e. a tie that the encoder's own 1e-4 rounding decides, in the reference's ORT-vs-eager gap as
 # much as here — and on at most one frame per thousand.  Every other case is strict.
 NEAR_TIE = 5e-5
+# log-mel (log domain): log(x + 1e-7) amplifies the rounding of powers near the floor.  Observed maxima (printed by the
+# tests): 2.7e-3 on the stress signal built for it — a tone 70 dB above the noise, i.e. bins 7 decades below their
+# neighbour through a split-precision DFT — and <= 2.7e-4 on every other signal; in the linear domain <= 6.2e-6 of the
+# power range everywhere (bound 1e-5).  The bound is 2x the worst case.
+LOGMEL_TOL = 5e-3
 SR = 16000
 
 
@@ -94,9 +99,12 @@ def test_front_end_taps(engine, weights, consts):
     # log-mel: fp32 DFT against the same tables; log() of tiny powers amplifies rounding, so compare
     # in the linear domain where the reference's own 1e-7 floor lives
     ref = taps["logmel"].numpy()
-    assert np.abs(np.exp(logmel) - np.exp(ref)).max() <= 1e-5 * max(1.0, float(np.exp(ref).max()))
-    assert np.abs(logmel - ref).max() <= 5e-3
-    assert np.abs(engine.read_tap("lfr") - taps["lfr"].numpy()).max() <= 5e-3
+    lin = float(np.abs(np.exp(logmel) - np.exp(ref)).max() / max(1.0, float(np.exp(ref).max())))
+    lg = float(np.abs(logmel - ref).max())
+    print(f"[front end/{engine.precision}] log-mel max |d| {lg:.3e} (log domain), {lin:.3e} of the power range (linear domain)")
+    assert lin <= 1e-5
+    assert lg <= LOGMEL_TOL
+    assert np.abs(engine.read_tap("lfr") - taps["lfr"].numpy()).max() <= LOGMEL_TOL
     for name in ("layer0", "layer1", "layer49"):
         _act_close(engine.read_tap(name), taps[name].numpy(), engine.precision, name)
 
@@ -134,9 +142,12 @@ def test_tensor_core_front_end_matches_oracle_and_cuda_core_front_end(weights, c
             got[mode] = eng.read_tap("logmel")
         finally:
             eng.close()
-        assert np.abs(np.exp(got[mode]) - np.exp(ref)).max() <= 1e-5 * max(1.0, float(np.exp(ref).max())), mode
-        assert np.abs(got[mode] - ref).max() <= 5e-3, mode
-    assert np.abs(got["tc"] - got["simt"]).max() <= 5e-3
+        lin = float(np.abs(np.exp(got[mode]) - np.exp(ref)).max() / max(1.0, float(np.exp(ref).max())))
+        lg = float(np.abs(got[mode] - ref).max())
+        print(f"[front end {kind}/{mode}] log-mel max |d| {lg:.3e} (log domain), {lin:.3e} of the power range")
+        assert lin <= 1e-5, mode
+        assert lg <= LOGMEL_TOL, mode
+    assert np.abs(got["tc"] - got["simt"]).max() <= LOGMEL_TOL
 
 
 def test_mixed_length_batch_rows_are_independent(engine, weights, consts):
